@@ -1,0 +1,288 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): C-ABI harness around the reference's OWN solver classes, compiled from
+// /root/reference UNMODIFIED (see oracle/Makefile).  It builds a scene directly through Simulation::addFluidModel /
+// BoundaryModel_Akinci2012::initModel in the order SimulatorBase does (Simulator/SimulatorBase.cpp:432-577:
+// Simulation::init -> fluid models -> parameters/simulationMethod -> boundary models -> setSimulationInitialized ->
+// StaticBoundarySimulator::deferredInit (StaticBoundarySimulator.cpp:181-199)), bypassing SimulatorBase, the scene
+// loader, PBD, GUI and Partio, none of which are on the hot path.  One Real per shared object
+// (libsplish_ref_f32.so: float + AVX variant, libsplish_ref_f64.so: double + scalar variant).
+// Used by tests/ (parity checker) and by bench.py's cpu_baseline / --impl reference legs only.
+#include "SPlisHSPlasH/Common.h"
+#include "SPlisHSPlasH/Simulation.h"
+#include "SPlisHSPlasH/TimeManager.h"
+#include "SPlisHSPlasH/TimeStep.h"
+#include "SPlisHSPlasH/FluidModel.h"
+#include "SPlisHSPlasH/BoundaryModel_Akinci2012.h"
+#include "SPlisHSPlasH/StaticRigidBody.h"
+#include "SPlisHSPlasH/DFSPH/TimeStepDFSPH.h"
+#include "Utilities/Timing.h"
+#include "Utilities/Counting.h"
+#include "Utilities/Logger.h"
+#include <chrono>
+#include <cstring>
+#include <omp.h>
+
+INIT_LOGGING
+INIT_TIMING
+INIT_COUNTING
+
+using namespace SPH;
+
+namespace {
+	double g_step_seconds = 0.0;
+	std::string g_err;
+
+	const Real* fieldPtr(FluidModel* fm, const char* name, unsigned int i)
+	{
+		const FieldDescription& f = fm->getField(name);
+		return (const Real*)f.getFct(i);
+	}
+}
+
+extern "C" {
+
+int ref_sizeof_real() { return (int)sizeof(Real); }
+int ref_uses_avx()
+{
+#ifdef USE_AVX
+	return 1;
+#else
+	return 0;
+#endif
+}
+int ref_num_threads() { return omp_get_max_threads(); }
+void ref_set_num_threads(int n) { omp_set_num_threads(n); }
+
+/* Simulation::init (Simulation.cpp:131-152). */
+int ref_create(double particleRadius)
+{
+	if (Simulation::hasCurrent()) return -1;
+	Utilities::Timing::m_dontPrintTimes = true;
+	Simulation* sim = Simulation::getCurrent();
+	sim->init(static_cast<Real>(particleRadius), false);
+	return 0;
+}
+
+/* Simulation::addFluidModel (Simulation.cpp:684-689); nMaxEmitterParticles = 0. */
+int ref_add_fluid(const Real* x, const Real* v, unsigned int n, double density0)
+{
+	Simulation* sim = Simulation::getCurrent();
+	std::vector<Vector3r> xs(n), vs(n);
+	std::vector<unsigned int> ids(n, 0u);
+	for (unsigned int i = 0; i < n; i++)
+	{
+		xs[i] = Vector3r(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+		vs[i] = v ? Vector3r(v[3 * i], v[3 * i + 1], v[3 * i + 2]) : Vector3r::Zero();
+	}
+	const unsigned int idx = sim->numberOfFluidModels();
+	sim->addFluidModel("Fluid" + std::to_string(idx), n, xs.data(), vs.data(), ids.data(), 0);
+	FluidModel* fm = sim->getFluidModel(idx);
+	fm->setDensity0(static_cast<Real>(density0));
+	fm->setViscosityMethod(0u);   // no non-pressure forces
+	return (int)idx;
+}
+
+/* Configuration step: boundaryHandlingMethod Akinci2012, simulationMethod DFSPH (creates TimeStepDFSPH,
+   Simulation.cpp:577-583), then the kernel choice is re-applied AFTER the method (SURVEY.md 3.4 ordering trap).
+   kernel: 0 = cubic, 4 = precomputed cubic (the DFSPH default). */
+int ref_configure(int kernel, int gradKernel)
+{
+	Simulation* sim = Simulation::getCurrent();
+	sim->setValue<int>(Simulation::BOUNDARY_HANDLING_METHOD, Simulation::ENUM_AKINCI2012);
+	sim->setValue<int>(Simulation::SIMULATION_METHOD, Simulation::ENUM_SIMULATION_DFSPH);
+	sim->setValue<int>(Simulation::KERNEL_METHOD, kernel);
+	sim->setValue<int>(Simulation::GRAD_KERNEL_METHOD, gradKernel);
+	return 0;
+}
+
+/* Static Akinci2012 boundary (StaticBoundarySimulator.cpp:146-152 + BoundaryModel_Akinci2012::initModel). */
+int ref_add_boundary(const Real* x, unsigned int n)
+{
+	Simulation* sim = Simulation::getCurrent();
+	std::vector<Vector3r> xs(n);
+	for (unsigned int i = 0; i < n; i++) xs[i] = Vector3r(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+	StaticRigidBody* rb = new StaticRigidBody();
+	rb->setPosition0(Vector3r::Zero());
+	rb->setPosition(Vector3r::Zero());
+	rb->setRotation0(Quaternionr::Identity());
+	rb->setRotation(Quaternionr::Identity());
+	BoundaryModel_Akinci2012* bm = new BoundaryModel_Akinci2012();
+	bm->initModel(rb, n, xs.data());
+	sim->addBoundaryModel(bm);
+	return (int)sim->numberOfBoundaryModels() - 1;
+}
+
+/* SimulatorBase::deferredInit tail (SimulatorBase.cpp:575-576) + StaticBoundarySimulator::deferredInit. */
+int ref_finalize()
+{
+	Simulation* sim = Simulation::getCurrent();
+	sim->setSimulationInitialized(true);
+	sim->performNeighborhoodSearchSort();
+	sim->updateBoundaryVolume();
+	return 0;
+}
+
+int ref_set_real(const char* name, double v)
+{
+	Simulation* sim = Simulation::getCurrent();
+	TimeStepDFSPH* ts = static_cast<TimeStepDFSPH*>(sim->getTimeStep());
+	const std::string s(name);
+	if (s == "timeStepSize") TimeManager::getCurrent()->setTimeStepSize(static_cast<Real>(v));
+	else if (s == "maxError") ts->setValue<Real>(TimeStepDFSPH::MAX_ERROR, static_cast<Real>(v));
+	else if (s == "maxErrorV") ts->setValue<Real>(TimeStepDFSPH::MAX_ERROR_V, static_cast<Real>(v));
+	else if (s == "cflFactor") sim->setValue<Real>(Simulation::CFL_FACTOR, static_cast<Real>(v));
+	else if (s == "cflMinTimeStepSize") sim->setValue<Real>(Simulation::CFL_MIN_TIMESTEPSIZE, static_cast<Real>(v));
+	else if (s == "cflMaxTimeStepSize") sim->setValue<Real>(Simulation::CFL_MAX_TIMESTEPSIZE, static_cast<Real>(v));
+	else return -1;
+	return 0;
+}
+
+int ref_set_int(const char* name, int v)
+{
+	Simulation* sim = Simulation::getCurrent();
+	TimeStepDFSPH* ts = static_cast<TimeStepDFSPH*>(sim->getTimeStep());
+	const std::string s(name);
+	if (s == "minIterations") ts->setValue<unsigned int>(TimeStepDFSPH::MIN_ITERATIONS, (unsigned int)v);
+	else if (s == "maxIterations") ts->setValue<unsigned int>(TimeStepDFSPH::MAX_ITERATIONS, (unsigned int)v);
+	else if (s == "maxIterationsV") ts->setValue<unsigned int>(TimeStepDFSPH::MAX_ITERATIONS_V, (unsigned int)v);
+	else if (s == "enableDivergenceSolver") ts->setValue<bool>(TimeStepDFSPH::USE_DIVERGENCE_SOLVER, v != 0);
+	else if (s == "cflMethod") sim->setValue<int>(Simulation::CFL_METHOD, v);
+	else if (s == "enableZSort") sim->setValue<bool>(Simulation::ENABLE_Z_SORT, v != 0);
+	else if (s == "stepsPerZSort") sim->setValue<unsigned int>(Simulation::STEPS_PER_Z_SORT, (unsigned int)v);
+	else return -1;
+	return 0;
+}
+
+int ref_set_gravity(double gx, double gy, double gz)
+{
+	Real g[3] = { static_cast<Real>(gx), static_cast<Real>(gy), static_cast<Real>(gz) };
+	Simulation::getCurrent()->setVecValue<Real>(Simulation::GRAVITATION, g);
+	return 0;
+}
+
+/* TimeStepDFSPH::step() (TimeStepDFSPH.cpp:117-249), n times; wall time accumulated. */
+int ref_step(int n)
+{
+	Simulation* sim = Simulation::getCurrent();
+	for (int k = 0; k < n; k++)
+	{
+		auto t0 = std::chrono::high_resolution_clock::now();
+		sim->getTimeStep()->step();
+		auto t1 = std::chrono::high_resolution_clock::now();
+		g_step_seconds += std::chrono::duration<double>(t1 - t0).count();
+	}
+	return 0;
+}
+
+double ref_step_seconds() { return g_step_seconds; }
+void ref_reset_step_seconds() { g_step_seconds = 0.0; }
+
+/* Average of one of the reference's own START_TIMING timers (Utilities/Timing.h), in ms; -1 if unknown. */
+double ref_avg_timer_ms(const char* name)
+{
+	for (auto& kv : Utilities::Timing::m_averageTimes)
+		if (kv.second.name == name && kv.second.counter > 0) return kv.second.totalTime / kv.second.counter;
+	return -1.0;
+}
+
+/* Neighbour search + density only (what ReadWriteStateTests.cpp:349-350 does). */
+int ref_search_and_density()
+{
+	Simulation* sim = Simulation::getCurrent();
+	sim->performNeighborhoodSearch();
+	for (unsigned int m = 0; m < sim->numberOfFluidModels(); m++) sim->getTimeStep()->computeDensities(m);
+	return 0;
+}
+
+unsigned int ref_num_particles(int fluid) { return Simulation::getCurrent()->getFluidModel(fluid)->numActiveParticles(); }
+unsigned int ref_num_boundary_particles(int b) { return static_cast<BoundaryModel_Akinci2012*>(Simulation::getCurrent()->getBoundaryModel(b))->numberOfParticles(); }
+double ref_time() { return TimeManager::getCurrent()->getTime(); }
+double ref_time_step_size() { return TimeManager::getCurrent()->getTimeStepSize(); }
+int ref_iterations() { return Simulation::getCurrent()->getTimeStep()->getValue<unsigned int>(TimeStepDFSPH::SOLVER_ITERATIONS); }
+int ref_iterations_v() { return Simulation::getCurrent()->getTimeStep()->getValue<unsigned int>(TimeStepDFSPH::SOLVER_ITERATIONS_V); }
+double ref_w_zero() { return Simulation::getCurrent()->W_zero(); }
+double ref_fluid_volume(int fluid) { return Simulation::getCurrent()->getFluidModel(fluid)->getVolume(0); }
+int ref_kernel() { return Simulation::getCurrent()->getKernel(); }
+
+/* Field names are the reference's own FieldDescription names (FluidModel.cpp:60-66, TimeStepDFSPH.cpp:49-53):
+   "position", "velocity", "density", "factor", "advected density", "p / rho^2", "p_v / rho^2",
+   "pressure acceleration"; plus "acceleration".  dim = 1 or 3.  Output in current (z-sorted) array order. */
+int ref_get_field(int fluid, const char* name, Real* out, int dim)
+{
+	FluidModel* fm = Simulation::getCurrent()->getFluidModel(fluid);
+	const unsigned int n = fm->numActiveParticles();
+	if (std::string(name) == "acceleration")
+	{
+		for (unsigned int i = 0; i < n; i++) for (int k = 0; k < 3; k++) out[3 * i + k] = fm->getAcceleration(i)[k];
+		return 0;
+	}
+	for (unsigned int i = 0; i < n; i++)
+	{
+		const Real* p = fieldPtr(fm, name, i);
+		for (int k = 0; k < dim; k++) out[dim * i + k] = p[k];
+	}
+	return 0;
+}
+
+int ref_get_ids(int fluid, unsigned int* out)
+{
+	FluidModel* fm = Simulation::getCurrent()->getFluidModel(fluid);
+	for (unsigned int i = 0; i < fm->numActiveParticles(); i++) out[i] = fm->getParticleId(i);
+	return 0;
+}
+
+/* Overwrite state (used to start reference and device runs from an identical, non-trivial state). */
+int ref_set_state(int fluid, const Real* x, const Real* v)
+{
+	FluidModel* fm = Simulation::getCurrent()->getFluidModel(fluid);
+	for (unsigned int i = 0; i < fm->numActiveParticles(); i++)
+	{
+		if (x) fm->getPosition(i) = Vector3r(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+		if (v) fm->getVelocity(i) = Vector3r(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+	}
+	return 0;
+}
+
+int ref_get_boundary(int b, Real* x, Real* V)
+{
+	BoundaryModel_Akinci2012* bm = static_cast<BoundaryModel_Akinci2012*>(Simulation::getCurrent()->getBoundaryModel(b));
+	for (unsigned int i = 0; i < bm->numberOfParticles(); i++)
+	{
+		if (x) for (int k = 0; k < 3; k++) x[3 * i + k] = bm->getPosition(i)[k];
+		if (V) V[i] = bm->getVolume(i);
+	}
+	return 0;
+}
+
+/* Neighbour counts of fluid set `fluid` against point set `pid` (valid after a step / search). */
+int ref_neighbor_counts(int fluid, int pid, unsigned int* counts)
+{
+	Simulation* sim = Simulation::getCurrent();
+	const unsigned int n = sim->getFluidModel(fluid)->numActiveParticles();
+	for (unsigned int i = 0; i < n; i++) counts[i] = sim->numberOfNeighbors(fluid, pid, i);
+	return 0;
+}
+
+/* CSR fill; offsets has n+1 entries (caller computes from counts), idx receives neighbour indices (array order). */
+int ref_neighbor_lists(int fluid, int pid, const unsigned long long* offsets, unsigned int* idx)
+{
+	Simulation* sim = Simulation::getCurrent();
+	const unsigned int n = sim->getFluidModel(fluid)->numActiveParticles();
+	#pragma omp parallel for schedule(static)
+	for (int i = 0; i < (int)n; i++)
+	{
+		const unsigned int c = sim->numberOfNeighbors(fluid, pid, i);
+		for (unsigned int k = 0; k < c; k++) idx[offsets[i] + k] = sim->getNeighbor(fluid, pid, i, k);
+	}
+	return 0;
+}
+
+int ref_destroy()
+{
+	if (!Simulation::hasCurrent()) return 0;
+	delete Simulation::getCurrent();   // also deletes TimeManager, models (+ their rigid bodies), time step (Simulation.cpp:91-110)
+	g_step_seconds = 0.0;
+	Utilities::Timing::m_averageTimes.clear();
+	return 0;
+}
+
+}

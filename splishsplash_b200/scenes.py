@@ -1,0 +1,135 @@
+"""Synthetic scene generators for the DFSPH hot path.
+
+No RNG anywhere: the particle distribution is the lattice itself, so a scene is fully described by its integer
+lattice counts, the particle radius and the dtype.
+
+* ``fluid_block``   restates the reference's ``SimulatorBase::createFluidBlocks`` (Simulator/SimulatorBase.cpp:1418-1526)
+  for denseMode 0 (regular lattice) and denseMode 1: spacing d = 2r, first particle at ``min + d``,
+  ``steps = round(L/d) - 1`` per axis, loop order x outer, y, z inner, arithmetic in ``Real``.
+* ``box_boundary``  single layer of Akinci2012 boundary particles on the faces of an axis-aligned box
+  (regular grid, default spacing 1.5 r).  The reference samples meshes (RegularTriangleSampling); here the box is
+  sampled directly, which is the same kind of input for ``BoundaryModel_Akinci2012::initModel``
+  (SPlisHSPlasH/BoundaryModel_Akinci2012.cpp:77-110).
+* ``dam_break``     the measurement scene of BASELINE.json configs 2-5: fluid block in the first third of a closed tank.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# BASELINE.json / SURVEY.md 8d named particle counts -> lattice counts (x, y, z)
+NAMED_BLOCKS = {
+    "tiny": (10, 12, 10),          # 1 200      unit-test size
+    "small": (20, 24, 20),         # 9 600
+    "64k": (40, 40, 40),           # 64 000
+    "1M": (100, 100, 100),         # 1 000 000  config 2
+    "10M": (216, 216, 215),        # 10 031 040 configs 3 and 5 (per GPU)
+    "50M": (464, 232, 464),        # 49 948 672 config 4
+}
+
+
+def fluid_lattice(counts, radius, start, dtype=np.float32):
+    """Regular lattice with ``counts`` = (nx, ny, nz) particles, spacing 2r, first particle at ``start``.
+
+    Position arithmetic follows SimulatorBase.cpp:1484 (``Vector3r(j*xshift, k*yshift, l*diam) + start`` in Real)."""
+    dt = np.dtype(dtype).type
+    nx, ny, nz = (int(c) for c in counts)
+    diam = dt(2.0) * dt(radius)
+    ax = [(np.arange(n, dtype=dtype) * diam + dt(s)).astype(dtype) for n, s in zip((nx, ny, nz), start)]
+    x = np.empty((nx, ny, nz, 3), dtype=dtype)
+    x[..., 0] = ax[0][:, None, None]
+    x[..., 1] = ax[1][None, :, None]
+    x[..., 2] = ax[2][None, None, :]
+    return x.reshape(-1, 3)
+
+
+def fluid_block(box_min, box_max, radius, dtype=np.float32, dense_mode=0):
+    """Restatement of ``createFluidBlocks`` (Simulator/SimulatorBase.cpp:1418-1526), denseMode 0 or 1, no transform."""
+    dt = np.dtype(dtype).type
+    r = dt(radius)
+    diam = dt(2.0) * r
+    xshift = diam
+    yshift = diam
+    if dense_mode == 1:
+        yshift = dt(np.sqrt(dt(3.0)) * r + dt(1.0e-9))
+    elif dense_mode != 0:
+        raise ValueError("dense_mode 0 or 1 only")
+    bmin = np.asarray(box_min, dtype=dtype)
+    bmax = np.asarray(box_max, dtype=dtype)
+    diff = (bmax - bmin).astype(dtype)
+    if dense_mode == 1:
+        diff[0] -= diam
+        diff[2] -= diam
+    # C round(): half away from zero
+    cround = lambda v: int(np.floor(abs(float(v)) + 0.5) * (1 if v >= 0 else -1))
+    sx = cround(diff[0] / xshift) - 1
+    sy = cround(diff[1] / yshift) - 1
+    sz = cround(diff[2] / diam) - 1
+    if sx <= 1 or sy <= 1 or sz <= 1:
+        return np.zeros((0, 3), dtype=dtype)
+    start = (bmin + diam).astype(dtype)
+    j = np.arange(sx, dtype=dtype)[:, None, None]
+    k = np.arange(sy, dtype=dtype)[None, :, None]
+    l = np.arange(sz, dtype=dtype)[None, None, :]
+    x = np.empty((sx, sy, sz, 3), dtype=dtype)
+    x[..., 0] = (j * xshift).astype(dtype) + start[0]
+    x[..., 1] = (k * yshift).astype(dtype) + start[1]
+    x[..., 2] = (l * diam).astype(dtype) + start[2]
+    if dense_mode == 1:
+        even = (np.arange(sy) % 2 == 0)[None, :, None]
+        x[..., 2] = np.where(even, x[..., 2] + r, x[..., 2]).astype(dtype)
+        x[..., 0] = np.where(~even, x[..., 0] + r, x[..., 0]).astype(dtype)
+    return x.reshape(-1, 3)
+
+
+def box_boundary(box_min, box_max, radius, dtype=np.float32, spacing_factor=1.5):
+    """One layer of boundary particles on the six faces of an axis-aligned box, no duplicates on edges."""
+    bmin = np.asarray(box_min, dtype=np.float64)
+    bmax = np.asarray(box_max, dtype=np.float64)
+    s = spacing_factor * float(radius)
+    n = [max(int(round((bmax[k] - bmin[k]) / s)), 1) for k in range(3)]
+    ax = [np.linspace(bmin[k], bmax[k], n[k] + 1) for k in range(3)]
+
+    def grid(a, b, c):
+        g = np.empty((len(a), len(b), len(c), 3), dtype=np.float64)
+        g[..., 0] = a[:, None, None]
+        g[..., 1] = b[None, :, None]
+        g[..., 2] = c[None, None, :]
+        return g.reshape(-1, 3)
+
+    parts = [
+        grid(ax[0][[0, -1]], ax[1], ax[2]),                 # x faces (own all their edges)
+        grid(ax[0][1:-1], ax[1][[0, -1]], ax[2]),           # y faces minus x edges
+        grid(ax[0][1:-1], ax[1][1:-1], ax[2][[0, -1]]),     # z faces minus x and y edges
+    ]
+    return np.ascontiguousarray(np.concatenate(parts, axis=0).astype(dtype))
+
+
+def dam_break(counts="tiny", radius=0.025, dtype=np.float32, tank_x_factor=3.0, tank_y_factor=1.5,
+              spacing_factor=1.5, x_offset=0.0):
+    """Dam-break block in a closed tank.
+
+    ``counts``: key of NAMED_BLOCKS or an (nx, ny, nz) tuple.  The block's bounding box starts at the tank corner, so the
+    nearest fluid particle sits one diameter from each adjacent wall.  Returns a dict with ``fluid_x`` (N,3),
+    ``boundary_x`` (Nb,3), ``radius``, ``counts``, ``tank_min``, ``tank_max``."""
+    if isinstance(counts, str):
+        counts = NAMED_BLOCKS[counts]
+    nx, ny, nz = counts
+    d = 2.0 * radius
+    block = np.array([(nx + 1) * d, (ny + 1) * d, (nz + 1) * d])
+    tmin = np.array([x_offset, 0.0, 0.0])
+    tmax = tmin + np.array([tank_x_factor * block[0], tank_y_factor * block[1], block[2]])
+    fluid = fluid_lattice(counts, radius, tmin + d, dtype)
+    bnd = box_boundary(tmin, tmax, radius, dtype, spacing_factor)
+    return {"fluid_x": fluid, "boundary_x": bnd, "radius": float(radius), "counts": tuple(counts),
+            "tank_min": tmin, "tank_max": tmax}
+
+
+def rw_state_scene(dtype=np.float32):
+    """Geometry of the reference's only shipped DFSPH + Akinci2012 + deterministic-sampling scene,
+    data/Scenes/ReadWriteStateTest.json: box 1 x 1.5 x 1 centred at (0, 0.75, 0), fluid block
+    [-0.25,0,-0.25]-[0.25,1,0.25] in denseMode 1, r = 0.025 (viscosity/vorticity off)."""
+    r = 0.025
+    fluid = fluid_block([-0.25, 0.0, -0.25], [0.25, 1.0, 0.25], r, dtype, dense_mode=1)
+    bnd = box_boundary([-0.5, 0.0, -0.5], [0.5, 1.5, 0.5], r, dtype)
+    return {"fluid_x": fluid, "boundary_x": bnd, "radius": r, "counts": None,
+            "tank_min": np.array([-0.5, 0.0, -0.5]), "tank_max": np.array([0.5, 1.5, 0.5])}
