@@ -1,0 +1,182 @@
+/* dfsph_b200.h -- C ABI of the B200-native DFSPH hot path (neighbourhood search + DFSPH pressure-solver loop).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  One `Real` per shared object,
+ * matching the reference's compile-time Real (SPlisHSPlasH/Common.h:6-24):
+ *     libdfsph_b200_f32.so  Real = float   -> behaviour of the reference's float+AVX solver variant
+ *                                             (SPlisHSPlasH/DFSPH/TimeStepDFSPH.cpp:733-1100)
+ *     libdfsph_b200_f64.so  Real = double  -> behaviour of the reference's scalar solver variant
+ *                                             (SPlisHSPlasH/DFSPH/TimeStepDFSPH.cpp:1104-1421)
+ * All Real* arguments are `float*` in the f32 library and `double*` in the f64 library (dfsph_b200_sizeof_real()).
+ *
+ * Every entry point returns 0 on success or a negative dfsph_b200_status; dfsph_b200_last_error() gives text.
+ * A context is single-caller (like the reference: TimeStep::step() is called from one thread,
+ * Simulator/SimulatorBase.cpp:920,970) and owns all device memory; host pointers are never retained past a call.
+ * There is NO CPU fallback: without a CUDA device dfsph_b200_create() fails with DFSPH_B200_ERR_CUDA.
+ *
+ * Reference interfaces each entry point replaces are cited per function (paths relative to the reference root).
+ */
+#ifndef DFSPH_B200_H
+#define DFSPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dfsph_b200_ctx dfsph_b200_ctx;
+
+typedef enum {
+    DFSPH_B200_OK = 0,
+    DFSPH_B200_ERR_INVALID = -1,      /* bad argument / call order */
+    DFSPH_B200_ERR_CUDA = -2,         /* CUDA runtime error (sticky in the ctx) */
+    DFSPH_B200_ERR_CAPACITY = -3,     /* neighbour-list / particle capacity exceeded (raise it in the config) */
+    DFSPH_B200_ERR_UNSUPPORTED = -4,  /* feature outside the hot-path scope (dynamic bodies, 2-D, multiphase, ...) */
+    DFSPH_B200_ERR_COMM = -5          /* multi-GPU exchange failed */
+} dfsph_b200_status;
+
+/* Kernel ids use the reference's enum values (SPlisHSPlasH/Simulation.cpp:215-253). */
+enum { DFSPH_B200_KERNEL_CUBIC = 0, DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC = 4 };
+
+/* Particle fields, named after the reference's FieldDescription names
+ * (SPlisHSPlasH/FluidModel.cpp:60-66, SPlisHSPlasH/DFSPH/TimeStepDFSPH.cpp:49-53). */
+typedef enum {
+    DFSPH_B200_FIELD_POSITION = 0,       /* "position"               Real[3] */
+    DFSPH_B200_FIELD_VELOCITY = 1,       /* "velocity"               Real[3] */
+    DFSPH_B200_FIELD_DENSITY = 2,        /* "density"                Real    */
+    DFSPH_B200_FIELD_FACTOR = 3,         /* "factor"                 Real    */
+    DFSPH_B200_FIELD_DENSITY_ADV = 4,    /* "advected density"       Real    */
+    DFSPH_B200_FIELD_KAPPA = 5,          /* "p / rho^2"              Real    (m_pressure_rho2)   */
+    DFSPH_B200_FIELD_KAPPA_V = 6,        /* "p_v / rho^2"            Real    (m_pressure_rho2_V) */
+    DFSPH_B200_FIELD_PRESSURE_ACCEL = 7, /* "pressure acceleration"  Real[3] */
+    DFSPH_B200_FIELD_ID = 8,             /* "id"                     uint32  (original particle index) */
+    DFSPH_B200_FIELD_STATE = 9,          /* "state"                  uint32  (0 Active, 1 AnimatedByEmitter, 2 Fixed) */
+    DFSPH_B200_FIELD_BOUNDARY_VOLUME = 10, /* BoundaryModel_Akinci2012::m_V, Real, in the order boundaries were added */
+    DFSPH_B200_FIELD_NUM_NEIGHBORS = 11  /* uint32: fluid + boundary neighbour count used by the deficiency test */
+} dfsph_b200_field;
+
+typedef struct {
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t kernel;                 /* Simulation "kernel"/"gradKernel": 0 cubic, 4 precomputed cubic (DFSPH default,
+                                       Simulation.cpp:579-582).  Honoured by the f64 library everywhere; the f32 library
+                                       mirrors the AVX build: solver sums always use the analytic cubic kernel
+                                       (TimeStep.cpp:80, TimeStepDFSPH.cpp:789) and `kernel` only selects the kernel of
+                                       the boundary-volume initialisation (BoundaryModel_Akinci2012.cpp:61-72). */
+    double particle_radius;         /* Simulation "particleRadius"; support radius = 4 r (Simulation.cpp:283) */
+    uint64_t max_fluid_particles;   /* device capacity; 0 = size of the first set_fluid call */
+    int32_t max_fluid_neighbors;    /* per-particle neighbour-table capacity, fluid set   (0 = default 64) */
+    int32_t max_boundary_neighbors; /* per-particle neighbour-table capacity, boundary set (0 = default 64) */
+    double domain_min[3];           /* cell-grid extent; if min == max it is derived from the particle sets at */
+    double domain_max[3];           /*   the first step (particles that leave it are clamped to the edge cells) */
+    int32_t rank;                   /* multi-GPU slab decomposition along x: this context's slab (0 for single GPU) */
+    int32_t world_size;             /* number of slabs (1 for single GPU) */
+} dfsph_b200_config;
+
+/* TimeStepDFSPH / Simulation / TimeManager parameters, same names and defaults as the reference
+ * (TimeStepDFSPH.cpp:28-41,73-115; Simulation.cpp:67-88,163-277; TimeManager.cpp:12). */
+typedef struct {
+    double time_step_size;          /* TimeManager h, default 0.001 */
+    double gravitation[3];          /* default (0,-9.81,0) */
+    uint32_t min_iterations;        /* 2 */
+    uint32_t max_iterations;        /* 100 */
+    double max_error;               /* 0.01  (percent) */
+    uint32_t max_iterations_v;      /* 100 */
+    double max_error_v;             /* 0.1   (percent) */
+    int32_t enable_divergence_solver; /* 1 */
+    int32_t cfl_method;             /* 0 none, 1 standard, 2 iter (Simulation.cpp:395-413) */
+    double cfl_factor;              /* 0.5 */
+    double cfl_min_time_step_size;  /* 1e-4 */
+    double cfl_max_time_step_size;  /* 5e-3 */
+} dfsph_b200_params;
+
+typedef struct {
+    uint32_t iterations;            /* "iterations"  (pressure solver)   TimeStepDFSPH.cpp:343 */
+    uint32_t iterations_v;          /* "iterationsV" (divergence solver) TimeStepDFSPH.cpp:497 */
+    double avg_density_error;       /* last avg_density_err of the pressure solve   */
+    double avg_density_error_v;     /* last avg_density_err of the divergence solve */
+    double time_step_size;          /* h after updateTimeStepSize (used by the pressure solve of this step) */
+    double time;                    /* TimeManager time after the step */
+    uint32_t num_particles;
+    uint32_t max_neighbors;         /* largest fluid-neighbour count seen this step */
+    uint32_t gpu_launches;          /* kernels launched by this step */
+    float ms_search;                /* device time: cell sort + reorder + neighbour table (CUDA events) */
+    float ms_solver;                /* device time: everything after the search */
+} dfsph_b200_step_stats;
+
+int dfsph_b200_sizeof_real(void);
+const char* dfsph_b200_version(void);
+void dfsph_b200_default_config(dfsph_b200_config* cfg);
+void dfsph_b200_default_params(dfsph_b200_params* p);
+
+/* Replaces: `new TimeStepDFSPH()` + `new NeighborhoodSearch(supportRadius)` (Simulation.cpp:149,577-583). */
+int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out);
+int dfsph_b200_destroy(dfsph_b200_ctx* ctx);
+const char* dfsph_b200_last_error(const dfsph_b200_ctx* ctx);  /* ctx may be NULL: error of the last failed create */
+
+/* Replaces: FluidModel::initModel -> add_point_set(x, n, dynamic, search, find) (FluidModel.cpp:285-327) and
+ * SimulationDataDFSPH::init (DFSPH/SimulationDataDFSPH.cpp:22-60).  x, v: AoS Real[3*n] (Eigen DontAlign layout,
+ * Common.h:27); v, id, state may be NULL (zero velocity, id = index, Active).  kappa/kappa_v start at 0. */
+int dfsph_b200_set_fluid(dfsph_b200_ctx* ctx, uint64_t n, const void* x, const void* v,
+                         const uint32_t* id, const uint32_t* state, double density0, double volume);
+
+/* Replaces: BoundaryModel_Akinci2012::initModel -> add_point_set(x, n, dynamic=false, search=false, find=true)
+ * (BoundaryModel_Akinci2012.cpp:77-110).  May be called several times (one call per rigid body); bodies are
+ * concatenated on the device.  V may be NULL (then call dfsph_b200_compute_boundary_volume).  Dynamic / animated
+ * bodies are outside the scope: is_dynamic != 0 returns DFSPH_B200_ERR_UNSUPPORTED. */
+int dfsph_b200_add_boundary(dfsph_b200_ctx* ctx, uint64_t n, const void* x, const void* V, int is_dynamic);
+
+/* Replaces: Simulation::updateBoundaryVolume + BoundaryModel_Akinci2012::computeBoundaryVolume
+ * (Simulation.cpp:696-756, BoundaryModel_Akinci2012.cpp:48-75):  V_i = 1 / (W(0) + sum_{boundary j} W(x_i - x_j)). */
+int dfsph_b200_compute_boundary_volume(dfsph_b200_ctx* ctx);
+
+/* Replaces: GenParam setters of TimeStepDFSPH / Simulation / TimeManager (see dfsph_b200_params). */
+int dfsph_b200_set_params(dfsph_b200_ctx* ctx, const dfsph_b200_params* p);
+int dfsph_b200_get_params(const dfsph_b200_ctx* ctx, dfsph_b200_params* p);
+
+/* Replaces: TimeStepDFSPH::step() (DFSPH/TimeStepDFSPH.cpp:117-249) including
+ * Simulation::performNeighborhoodSearch (Simulation.cpp:606-619).  State stays resident on the device.
+ * stats may be NULL (then the call does not synchronise with the device). */
+int dfsph_b200_step(dfsph_b200_ctx* ctx, dfsph_b200_step_stats* stats);
+
+/* The same step through HOST buffers, as the reference-facing plugin does when host code touched the particle
+ * arrays: uploads x and v (AoS, in id order, i.e. row k = particle with id k), steps, downloads x and v into the
+ * same buffers and (if non-NULL) density into `density`.  Copies are inside the call. */
+int dfsph_b200_step_host(dfsph_b200_ctx* ctx, void* x_inout, void* v_inout, void* density_out,
+                         dfsph_b200_step_stats* stats);
+
+/* Replaces: the host-pointer accessors FluidModel::getPosition(i) ... / FieldDescription::getFct(i)
+ * (FluidModel.h:57-73,247-400).  Rows are in CURRENT device order (the order the search sorted the particles into;
+ * download DFSPH_B200_FIELD_ID to map rows to original indices) unless by_id != 0, in which case row k belongs to the
+ * particle whose id is k.  `bytes` must equal n * elemsize of the field. */
+int dfsph_b200_download(dfsph_b200_ctx* ctx, dfsph_b200_field field, void* dst, size_t bytes, int by_id);
+int dfsph_b200_upload(dfsph_b200_ctx* ctx, dfsph_b200_field field, const void* src, size_t bytes, int by_id);
+
+/* Replaces: NeighborhoodSearch::find_neighbors + PointSet::n_neighbors / neighbor_list
+ * (Simulation.cpp:617, Simulation.h:456-473) for set 0 (fluid) against set `other` (0 fluid, 1 boundary).
+ * Runs the search on the current positions if needed.  counts[n]; if idx != NULL, offsets[n+1] and idx[cap] receive a
+ * CSR table (lists ascending).  Fluid rows/indices are in current device order (see FIELD_ID); boundary indices are
+ * the order in which boundary particles were added.  Only for tests and non-ported host code -- the solver never
+ * materialises host-visible lists. */
+int dfsph_b200_neighbors(dfsph_b200_ctx* ctx, int other, uint32_t* counts, uint64_t* offsets, uint32_t* idx, uint64_t cap);
+
+/* Neighbour search + density only (what ReadWriteStateTests.cpp:349-350 exercises):
+ * Simulation::performNeighborhoodSearch(); TimeStep::computeDensities(0). */
+int dfsph_b200_search_and_density(dfsph_b200_ctx* ctx);
+
+uint64_t dfsph_b200_num_particles(const dfsph_b200_ctx* ctx);
+uint64_t dfsph_b200_num_boundary_particles(const dfsph_b200_ctx* ctx);
+
+/* Evaluate the device kernel functions W and gradW at n points r (AoS Real[3n]) -> W[n], gradW[3n].
+ * Lets the reference's Tests/Kernel/KernelTests.cpp checks run against the device implementations. */
+int dfsph_b200_eval_kernel(dfsph_b200_ctx* ctx, int kernel, uint64_t n, const void* r, void* W, void* gradW);
+
+/* Pinned host buffers for the host-buffer path (dfsph_b200_step_host) and an explicit stream synchronise. */
+void* dfsph_b200_alloc_pinned(size_t bytes);
+void dfsph_b200_free_pinned(void* p);
+int dfsph_b200_synchronize(dfsph_b200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFSPH_B200_H */

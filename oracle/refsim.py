@@ -31,11 +31,11 @@ FIELDS = {  # reference FieldDescription name -> dim
 class RefSim:
     """The reference's Simulation + TimeStepDFSPH driven through the C harness."""
 
-    def __init__(self, precision: str = "f64"):
+    def __init__(self, precision: str = "f64", lib_path: str | None = None):
         assert precision in ("f32", "f64")
         self.precision = precision
         self.dtype = np.float32 if precision == "f32" else np.float64
-        self.lib = C.CDLL(ref_lib_path(precision))
+        self.lib = C.CDLL(lib_path or ref_lib_path(precision))
         L = self.lib
         for name in ("ref_step_seconds", "ref_time", "ref_time_step_size", "ref_w_zero", "ref_avg_timer_ms"):
             getattr(L, name).restype = C.c_double
@@ -201,9 +201,9 @@ class RefSim:
         self.destroy()
 
 
-def build_ref_scene(scene, precision="f64", kernel=4, **params):
+def build_ref_scene(scene, precision="f64", kernel=4, lib_path=None, **params):
     """Create a RefSim for a ``splishsplash_b200.scenes`` scene dict."""
-    sim = RefSim(precision)
+    sim = RefSim(precision, lib_path)
     sim.create(scene["radius"])
     sim.add_fluid(scene["fluid_x"], scene.get("fluid_v"))
     sim.configure(kernel)

@@ -1,0 +1,138 @@
+// Shared types of the B200 DFSPH hot path.  One Real per shared object (-DDFSPH_DOUBLE selects double), mirroring
+// the reference's compile-time Real (SPlisHSPlasH/Common.h:6-24).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifdef DFSPH_DOUBLE
+typedef double Real;
+#define DFSPH_REAL_IS_DOUBLE 1
+#else
+typedef float Real;
+#define DFSPH_REAL_IS_DOUBLE 0
+#endif
+
+// 4-wide particle record: one 16 B (float) / 32 B (double) vector access per gather.
+struct alignas(4 * sizeof(Real)) Real4 { Real x, y, z, w; };
+struct Real3 { Real x, y, z; };
+
+__host__ __device__ __forceinline__ Real4 make_real4(Real x, Real y, Real z, Real w) { Real4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+// Vector loads.  ld_gather goes through the read-only (non-coherent) path: used for arrays that are not written by
+// the running kernel.  ld_plain is an ordinary (L1-cached) load for arrays with a benign in-kernel writer.
+__device__ __forceinline__ Real4 ld_gather(const Real4* p)
+{
+#if DFSPH_REAL_IS_DOUBLE
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return make_real4(a.x, a.y, b.x, b.y);
+#else
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    return make_real4(a.x, a.y, a.z, a.w);
+#endif
+}
+__device__ __forceinline__ Real4 ld_plain(const Real4* p)
+{
+#if DFSPH_REAL_IS_DOUBLE
+    const double2 a = *(reinterpret_cast<const double2*>(p));
+    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+    return make_real4(a.x, a.y, b.x, b.y);
+#else
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    return make_real4(a.x, a.y, a.z, a.w);
+#endif
+}
+__device__ __forceinline__ void st_real4(Real4* p, Real4 v)
+{
+#if DFSPH_REAL_IS_DOUBLE
+    reinterpret_cast<double2*>(p)[0] = make_double2(v.x, v.y);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v.z, v.w);
+#else
+    *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cell grid: cell edge S >= support radius R (S = R * (1 + 1e-5): two particles that pass the predicate
+// l2 < R*R are then at most one cell apart on every axis even with rounding in the cell computation, which is
+// done in double).  Cells are ordered in "blocked z-order": 8x8x8-cell blocks in row-major order (x slowest), cells
+// inside a block by their 9-bit Morton code.  Table size stays proportional to the domain (no power-of-two blow-up)
+// while the particles of any 2^k-aligned sub-brick are contiguous in memory.
+// ---------------------------------------------------------------------------------------------------------------
+struct GridDesc {
+    double ox, oy, oz;      // origin
+    double inv_cell;        // 1 / S
+    int nx, ny, nz;         // cells per axis
+    int nby, nbz;           // blocks per axis (y, z)
+    unsigned num_keys;      // nbx * nby * nbz * 512
+};
+
+__host__ __device__ __forceinline__ unsigned spread3(unsigned v)   // 3 bits -> bits 0,3,6
+{
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4);
+}
+__host__ __device__ __forceinline__ unsigned cell_key(int cx, int cy, int cz, const GridDesc& g)
+{
+    const unsigned b = ((unsigned)(cx >> 3) * (unsigned)g.nby + (unsigned)(cy >> 3)) * (unsigned)g.nbz + (unsigned)(cz >> 3);
+    const unsigned l = spread3((unsigned)cx & 7u) | (spread3((unsigned)cy & 7u) << 1) | (spread3((unsigned)cz & 7u) << 2);
+    return b * 512u + l;
+}
+__host__ __device__ __forceinline__ int cell_coord(Real x, double o, double inv, int n)
+{
+    const double t = ((double)x - o) * inv;
+    int c = (int)floor(t);
+    c = c < 0 ? 0 : c;
+    return c >= n ? n - 1 : c;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SPH constants (host-computed in Real exactly as the reference's setRadius functions do).
+// ---------------------------------------------------------------------------------------------------------------
+enum KernelMode { KM_CUBIC_AVX = 0, KM_CUBIC = 1, KM_LUT = 2 };
+
+struct SphConst {
+    Real R;            // support radius (4 r)
+    Real R2;           // R*R in Real: neighbour predicate threshold
+    Real invR;         // 1/R
+    Real invR2;        // invR*invR (CubicKernel_AVX::m_invRadius2)
+    Real k, l;         // cubic spline constants 8/(pi R^3), 48/(pi R^3)
+    Real W_zero;       // W(0) of the solver kernel
+    Real V;            // fluid particle volume (FluidModel::m_V)
+    Real density0;
+    Real lut_inv_step; // PrecomputedKernel::m_invStepSize
+    const Real* lutW;      // [10000]
+    const Real* lutGradW;  // [10001]
+    int mode;          // KernelMode used by the solver sums
+};
+
+// Solver control block, resident in device memory so that no host round trip is needed inside a step.
+struct Ctrl {
+    Real h;                 // TimeManager time step size (updated by the CFL kernel)
+    Real h_step;            // h captured at the start of the step (TimeStepDFSPH.cpp:121)
+    double time;
+    double err_sum;         // reduced density error of the last Jacobi pass
+    double avg_err;         // pressure solve
+    double avg_err_v;       // divergence solve
+    unsigned long long maxvel_bits;   // CFL: max |v + a h|^2 as ordered bits (non-negative IEEE values order like integers)
+    unsigned iter;          // running iteration counter of the current solve
+    unsigned iterations;    // result: pressure solver iterations
+    unsigned iterations_v;  // result: divergence solver iterations
+    int done;               // current solve finished
+    unsigned ticket;        // last-block election
+    unsigned overflow;      // neighbour-table capacity exceeded (value = needed capacity)
+    unsigned overflow_b;
+    unsigned max_nbr;
+    unsigned pad;
+};
+
+struct SolverParams {
+    Real gx, gy, gz;
+    Real max_error, max_error_v;      // percent
+    unsigned min_iter, max_iter, max_iter_v;
+    int cfl_method;
+    Real cfl_factor, cfl_min, cfl_max;
+    Real radius;                      // particle radius
+};
+
+#define DFSPH_BLOCK 256
+#define DFSPH_TILE 32

@@ -1,0 +1,1050 @@
+// C-ABI implementation + step orchestration of the B200 DFSPH hot path (see include/dfsph_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a [-DDFSPH_DOUBLE] -> libdfsph_b200_f32.so / libdfsph_b200_f64.so
+#include "../../include/dfsph_b200.h"
+#include "common.cuh"
+#include "sph_kernels.cuh"
+#include "search_kernels.cuh"
+#include "solver_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+static thread_local std::string g_create_error;
+
+struct dfsph_b200_ctx {
+    dfsph_b200_config cfg;
+    dfsph_b200_params par;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sticky = 0;
+
+    unsigned n = 0, cap = 0, ntiles_cap = 0;
+    unsigned Kf = 64, Kb = 64;
+    double density0 = 1000.0, volume = 0.0;
+
+    // fluid: double-buffered persistent state (search reorders from [cur] into [1-cur])
+    Real4* pos[2] = {nullptr, nullptr};
+    Real4* vel[2] = {nullptr, nullptr};
+    Real* kappa[2] = {nullptr, nullptr};
+    Real* kappa_v[2] = {nullptr, nullptr};
+    unsigned* id[2] = {nullptr, nullptr};
+    unsigned* state[2] = {nullptr, nullptr};
+    int cur = 0;        // buffers holding vel/kappa/kappa_v/id/state
+    int cur_pos = 0;    // buffer holding the current positions
+    Real4 *acc = nullptr, *bgrad = nullptr;
+    Real *density = nullptr, *factor = nullptr, *density_adv = nullptr;
+    unsigned *nnbr = nullptr, *cnt_f = nullptr, *cnt_b = nullptr, *tab_f = nullptr, *tab_b = nullptr;
+    unsigned *cell_key = nullptr, *cell_rank = nullptr, *sorted_idx = nullptr;
+    unsigned *cell_count = nullptr, *cell_start = nullptr, *scan_partial = nullptr;
+    unsigned keys_cap = 0, scratch_cap = 0;
+    bool tables_valid = false;   // neighbour table matches pos[cur_pos]
+
+    // boundary (static Akinci2012 particles, all bodies concatenated)
+    std::vector<Real4> h_bpos;
+    bool have_bvol = true;
+    unsigned nb = 0;
+    Real4* bpos = nullptr;
+    unsigned* borig = nullptr;
+    unsigned* bcell_start = nullptr;
+    bool boundary_dirty = true;
+
+    double bb_min[3], bb_max[3];
+    bool bb_valid = false;
+    GridDesc grid;
+    bool grid_valid = false;
+
+    SphConst sph;        // solver kernel
+    SphConst sph_bv;     // scalar kernel used by the boundary volume initialisation
+    Real *lutW = nullptr, *lutGradW = nullptr;
+    int solver_mode = KM_CUBIC_AVX, bv_mode = KM_LUT;
+
+    Ctrl* ctrl = nullptr;
+    Ctrl* h_ctrl = nullptr;      // pinned
+    double* partial = nullptr;
+    unsigned pred_iter = 2, pred_iter_v = 1;
+    unsigned launches = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    void* stage = nullptr;       // device staging for AoS transfers
+    size_t stage_bytes = 0;
+};
+
+#define CTX_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (ctx)->err = _b; return (code); } while (0)
+#define CUDA_TRY(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { (ctx)->sticky = 1; \
+    CTX_FAIL(ctx, DFSPH_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); } } while (0)
+#define CHECK_CTX(ctx) do { if (!(ctx)) return DFSPH_B200_ERR_INVALID; if ((ctx)->sticky) return DFSPH_B200_ERR_CUDA; } while (0)
+
+static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+template <typename T>
+static int dev_alloc(dfsph_b200_ctx* c, T** p, size_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) count = 1;
+    CUDA_TRY(c, cudaMalloc((void**)p, count * sizeof(T)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel constants, computed on the host in Real with the reference's own expression order
+// (CubicKernel::setRadius SPHKernels.h:25-35, CubicKernel_AVX::setRadius :713-740, PrecomputedKernel::setRadius :625-644)
+// ---------------------------------------------------------------------------------------------------------------
+static Real host_cubic_W(Real r, Real radius, Real k)
+{
+    Real res = 0.0;
+    const Real q = r / radius;
+    if (q <= 1.0) {
+        if (q <= 0.5) {
+            const Real q2 = q * q;
+            const Real q3 = q2 * q;
+            res = k * (static_cast<Real>(6.0) * q3 - static_cast<Real>(6.0) * q2 + static_cast<Real>(1.0));
+        } else {
+            res = k * (static_cast<Real>(2.0) * std::pow(static_cast<Real>(1.0) - q, static_cast<Real>(3.0)));
+        }
+    }
+    return res;
+}
+static Real host_cubic_gradW_x(Real rl, Real radius, Real l)   // x component of gradW((rl,0,0))
+{
+    Real res = 0.0;
+    const Real q = rl / radius;
+    if ((rl > 1.0e-9) && (q <= 1.0)) {
+        Real gradq = rl / rl;
+        gradq /= radius;
+        if (q <= 0.5) res = l * q * ((Real)3.0 * q - static_cast<Real>(2.0)) * gradq;
+        else { const Real factor = static_cast<Real>(1.0) - q; res = l * (-factor * factor) * gradq; }
+    }
+    return res;
+}
+
+static int setup_constants(dfsph_b200_ctx* c)
+{
+    const Real radius = static_cast<Real>(4.0) * static_cast<Real>(c->cfg.particle_radius);   // Simulation.cpp:283
+    const Real pi = static_cast<Real>(M_PI);
+    const Real h3 = radius * radius * radius;
+    SphConst s;
+    memset(&s, 0, sizeof(s));
+    s.R = radius;
+    s.R2 = radius * radius;
+#if DFSPH_REAL_IS_DOUBLE
+    s.invR = 1.0 / radius;
+    s.k = static_cast<Real>(8.0) / (pi * h3);
+    s.l = static_cast<Real>(48.0) / (pi * h3);
+#else
+    s.invR = 1.0f / radius;
+    s.k = 8.0f / static_cast<float>(pi * h3);
+    s.l = 48.0f / static_cast<float>(pi * h3);
+#endif
+    s.invR2 = s.invR * s.invR;
+    s.W_zero = host_cubic_W(0, radius, s.k);
+    s.V = static_cast<Real>(c->volume);
+    s.density0 = static_cast<Real>(c->density0);
+
+    // lookup tables (PrecomputedKernel<CubicKernel, 10000>)
+    std::vector<Real> W(LUT_RESOLUTION), G(LUT_RESOLUTION + 1);
+    const Real stepSize = radius / (Real)(LUT_RESOLUTION - 1);
+    s.lut_inv_step = static_cast<Real>(1.0) / stepSize;
+    for (unsigned i = 0; i < LUT_RESOLUTION; i++) {
+        const Real posX = stepSize * (Real)i;
+        W[i] = host_cubic_W(posX, radius, s.k);
+        if (posX > 1.0e-9) G[i] = host_cubic_gradW_x(posX, radius, s.l) / posX;
+        else G[i] = 0.0;
+    }
+    G[LUT_RESOLUTION] = 0.0;
+    if (dev_alloc(c, &c->lutW, LUT_RESOLUTION)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->lutGradW, LUT_RESOLUTION + 1)) return DFSPH_B200_ERR_CUDA;
+    CUDA_TRY(c, cudaMemcpy(c->lutW, W.data(), W.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->lutGradW, G.data(), G.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    s.lutW = c->lutW;
+    s.lutGradW = c->lutGradW;
+
+    const bool lut = (c->cfg.kernel == DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC);
+#if DFSPH_REAL_IS_DOUBLE
+    c->solver_mode = lut ? KM_LUT : KM_CUBIC;
+#else
+    c->solver_mode = KM_CUBIC_AVX;   // the AVX solver ignores the kernel setting
+#endif
+    c->bv_mode = lut ? KM_LUT : KM_CUBIC;
+    s.mode = c->solver_mode;
+    c->sph = s;
+    c->sph_bv = s;
+    c->sph_bv.mode = c->bv_mode;
+    return 0;
+}
+
+static SolverParams make_solver_params(const dfsph_b200_ctx* c)
+{
+    SolverParams sp;
+    sp.gx = (Real)c->par.gravitation[0]; sp.gy = (Real)c->par.gravitation[1]; sp.gz = (Real)c->par.gravitation[2];
+    sp.max_error = (Real)c->par.max_error; sp.max_error_v = (Real)c->par.max_error_v;
+    sp.min_iter = c->par.min_iterations; sp.max_iter = c->par.max_iterations; sp.max_iter_v = c->par.max_iterations_v;
+    sp.cfl_method = c->par.cfl_method;
+    sp.cfl_factor = (Real)c->par.cfl_factor; sp.cfl_min = (Real)c->par.cfl_min_time_step_size; sp.cfl_max = (Real)c->par.cfl_max_time_step_size;
+    sp.radius = (Real)c->cfg.particle_radius;
+    return sp;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int dfsph_b200_sizeof_real(void) { return (int)sizeof(Real); }
+const char* dfsph_b200_version(void) { return DFSPH_REAL_IS_DOUBLE ? "dfsph_b200 0.1 (f64, sm_100a)" : "dfsph_b200 0.1 (f32, sm_100a)"; }
+
+void dfsph_b200_default_config(dfsph_b200_config* cfg)
+{
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->kernel = DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC;
+    cfg->particle_radius = 0.025;
+    cfg->max_fluid_neighbors = 64;
+    cfg->max_boundary_neighbors = 64;
+    cfg->world_size = 1;
+}
+
+void dfsph_b200_default_params(dfsph_b200_params* p)
+{
+    memset(p, 0, sizeof(*p));
+    p->time_step_size = 0.001;
+    p->gravitation[1] = -9.81;
+    p->min_iterations = 2;
+    p->max_iterations = 100;
+    p->max_error = 0.01;
+    p->max_iterations_v = 100;
+    p->max_error_v = 0.1;
+    p->enable_divergence_solver = 1;
+    p->cfl_method = 1;
+    p->cfl_factor = 0.5;
+    p->cfl_min_time_step_size = 0.0001;
+    p->cfl_max_time_step_size = 0.005;
+}
+
+const char* dfsph_b200_last_error(const dfsph_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return DFSPH_B200_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->kernel != DFSPH_B200_KERNEL_CUBIC && cfg->kernel != DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC) {
+        g_create_error = "unsupported kernel (0 = cubic, 4 = precomputed cubic)";
+        return DFSPH_B200_ERR_UNSUPPORTED;
+    }
+    if (!(cfg->particle_radius > 0.0)) { g_create_error = "particle_radius must be > 0"; return DFSPH_B200_ERR_INVALID; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return DFSPH_B200_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return DFSPH_B200_ERR_INVALID; }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return DFSPH_B200_ERR_CUDA; }
+    dfsph_b200_ctx* c = new dfsph_b200_ctx();
+    c->cfg = *cfg;
+    dfsph_b200_default_params(&c->par);
+    c->Kf = cfg->max_fluid_neighbors > 0 ? (unsigned)cfg->max_fluid_neighbors : 64u;
+    c->Kb = cfg->max_boundary_neighbors > 0 ? (unsigned)cfg->max_boundary_neighbors : 64u;
+    int rc = 0;
+    do {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = -1; break; }
+        for (int k = 0; k < 3; ++k) if ((e = cudaEventCreate(&c->ev[k])) != cudaSuccess) { rc = -1; break; }
+        if (rc) break;
+        if ((e = cudaMalloc((void**)&c->ctrl, sizeof(Ctrl))) != cudaSuccess) { rc = -1; break; }
+        if ((e = cudaMemset(c->ctrl, 0, sizeof(Ctrl))) != cudaSuccess) { rc = -1; break; }
+        if ((e = cudaMallocHost((void**)&c->h_ctrl, sizeof(Ctrl))) != cudaSuccess) { rc = -1; break; }
+        memset(c->h_ctrl, 0, sizeof(Ctrl));
+    } while (0);
+    if (rc) { g_create_error = cudaGetErrorString(e); dfsph_b200_destroy(c); return DFSPH_B200_ERR_CUDA; }
+    *out = c;
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_destroy(dfsph_b200_ctx* c)
+{
+    if (!c) return DFSPH_B200_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->kappa[k]); cudaFree(c->kappa_v[k]); cudaFree(c->id[k]); cudaFree(c->state[k]);
+    }
+    cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
+    cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b);
+    cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
+    cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start);
+    cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
+    if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
+    for (int k = 0; k < 3; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return DFSPH_B200_OK;
+}
+
+uint64_t dfsph_b200_num_particles(const dfsph_b200_ctx* c) { return c ? c->n : 0; }
+uint64_t dfsph_b200_num_boundary_particles(const dfsph_b200_ctx* c) { return c ? c->nb : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+static void bbox_extend(dfsph_b200_ctx* c, const Real* x, uint64_t n)
+{
+    if (!c->bb_valid) { for (int k = 0; k < 3; ++k) { c->bb_min[k] = 1e300; c->bb_max[k] = -1e300; } c->bb_valid = true; }
+    for (uint64_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const double v = (double)x[3 * i + k];
+            if (v < c->bb_min[k]) c->bb_min[k] = v;
+            if (v > c->bb_max[k]) c->bb_max[k] = v;
+        }
+}
+
+static int ensure_stage(dfsph_b200_ctx* c, size_t bytes)
+{
+    if (bytes <= c->stage_bytes) return 0;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr; c->stage_bytes = 0;
+    CUDA_TRY(c, cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+static int ensure_scratch(dfsph_b200_ctx* c, unsigned count)
+{
+    if (count <= c->scratch_cap) return 0;
+    if (dev_alloc(c, &c->cell_key, count)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->cell_rank, count)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->sorted_idx, count)) return DFSPH_B200_ERR_CUDA;
+    c->scratch_cap = count;
+    return 0;
+}
+
+static int setup_grid(dfsph_b200_ctx* c)
+{
+    double lo[3], hi[3];
+    bool given = false;
+    for (int k = 0; k < 3; ++k) if (c->cfg.domain_max[k] > c->cfg.domain_min[k]) given = true;
+    const double S = (double)c->sph.R * (1.0 + 1.0e-5);
+    if (given) { for (int k = 0; k < 3; ++k) { lo[k] = c->cfg.domain_min[k]; hi[k] = c->cfg.domain_max[k]; } }
+    else {
+        if (!c->bb_valid) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "no particles: cannot derive the cell grid");
+        for (int k = 0; k < 3; ++k) { lo[k] = c->bb_min[k] - S; hi[k] = c->bb_max[k] + S; }
+    }
+    GridDesc g;
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+    g.inv_cell = 1.0 / S;
+    int nc[3];
+    for (int k = 0; k < 3; ++k) {
+        const double cells = std::ceil((hi[k] - lo[k]) / S);
+        if (cells > 8192.0) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "cell grid too large on axis %d (%g cells)", k, cells);
+        nc[k] = std::max(1, (int)cells);
+    }
+    g.nx = nc[0]; g.ny = nc[1]; g.nz = nc[2];
+    const unsigned nbx = div_up(g.nx, 8), nby = div_up(g.ny, 8), nbz = div_up(g.nz, 8);
+    g.nby = (int)nby; g.nbz = (int)nbz;
+    const unsigned long long keys = (unsigned long long)nbx * nby * nbz * 512ull;
+    if (keys > 1500000000ull) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "cell table too large (%llu cells)", keys);
+    g.num_keys = (unsigned)keys;
+    c->grid = g;
+    if (g.num_keys + 1 > c->keys_cap) {
+        if (dev_alloc(c, &c->cell_count, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->cell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->bcell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->scan_partial, div_up(g.num_keys, SCAN_CHUNK) + 8)) return DFSPH_B200_ERR_CUDA;
+        c->keys_cap = g.num_keys + 1;
+    }
+    c->grid_valid = true;
+    c->boundary_dirty = true;
+    c->tables_valid = false;
+    return 0;
+}
+
+// counting sort of `n` points at `pos` into the cell table `cell_start_out`; leaves the permutation in sorted_idx
+static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* cell_start_out)
+{
+    const GridDesc& g = c->grid;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaMemsetAsync(c->cell_count, 0, (size_t)g.num_keys * sizeof(unsigned), st));
+    if (n > 0) { k_cell_hash<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->cell_count, c->cell_key, c->cell_rank); c->launches++; }
+    const unsigned nparts = div_up(g.num_keys, SCAN_CHUNK);
+    k_scan_partials<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, g.num_keys, c->scan_partial);
+    k_scan_spine<<<1, SCAN_BLOCK, 0, st>>>(c->scan_partial, nparts);
+    k_scan_apply<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, g.num_keys, c->scan_partial, nparts, cell_start_out);
+    c->launches += 3;
+    if (n > 0) {
+        k_cell_scatter<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(c->cell_key, c->cell_rank, n, cell_start_out, c->sorted_idx);
+        k_cell_fix_order<<<div_up(g.num_keys, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(cell_start_out, g.num_keys, c->sorted_idx);
+        c->launches += 2;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_set_w(Real4* p, const Real* w, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i].w = w[i];
+}
+__global__ void k_iota(unsigned* p, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+static int finalize_boundary(dfsph_b200_ctx* c)
+{
+    if (!c->boundary_dirty) return 0;
+    const unsigned nb = (unsigned)c->h_bpos.size();
+    c->nb = nb;
+    const unsigned need = std::max(nb, 1u);
+    Real4* tmp = nullptr;
+    unsigned* tmp_orig = nullptr;
+    if (dev_alloc(c, &c->bpos, need)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->borig, need)) return DFSPH_B200_ERR_CUDA;
+    if (nb > 0) {
+        { int rs = ensure_scratch(c, nb); if (rs) return rs; }   // sorting scratch is sized for max(n, nb)
+        CUDA_TRY(c, cudaMalloc((void**)&tmp, (size_t)nb * sizeof(Real4)));
+        CUDA_TRY(c, cudaMalloc((void**)&tmp_orig, (size_t)nb * sizeof(unsigned)));
+        CUDA_TRY(c, cudaMemcpyAsync(tmp, c->h_bpos.data(), (size_t)nb * sizeof(Real4), cudaMemcpyHostToDevice, c->stream));
+        k_iota<<<div_up(nb, 256), 256, 0, c->stream>>>(tmp_orig, nb);
+    }
+    int rc = cell_sort(c, tmp, nb, c->bcell_start);
+    if (rc == 0 && nb > 0) {
+        k_reorder_boundary<<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->sorted_idx, tmp, tmp_orig, c->bpos, c->borig);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { c->sticky = 1; c->err = cudaGetErrorString(e); rc = DFSPH_B200_ERR_CUDA; }
+    }
+    if (tmp) cudaFree(tmp);
+    if (tmp_orig) cudaFree(tmp_orig);
+    if (rc) return rc;
+    c->boundary_dirty = false;
+    c->tables_valid = false;
+    return 0;
+}
+
+static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
+{
+    for (int k = 0; k < 2; ++k) {
+        if (dev_alloc(c, &c->pos[k], cap)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->vel[k], cap)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->kappa[k], cap)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->kappa_v[k], cap)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->id[k], cap)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->state[k], cap)) return DFSPH_B200_ERR_CUDA;
+    }
+    if (dev_alloc(c, &c->acc, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->bgrad, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->density, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->factor, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->density_adv, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->nnbr, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->cnt_f, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->cnt_b, cap)) return DFSPH_B200_ERR_CUDA;
+    const unsigned ntiles = div_up(cap, DFSPH_TILE);
+    c->ntiles_cap = ntiles;
+    if (dev_alloc(c, &c->tab_f, (size_t)ntiles * c->Kf * DFSPH_TILE)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->tab_b, (size_t)ntiles * c->Kb * DFSPH_TILE)) return DFSPH_B200_ERR_CUDA;
+    { int rs = ensure_scratch(c, cap); if (rs) return rs; }
+    if (dev_alloc(c, &c->partial, div_up(cap, DFSPH_BLOCK) + 1)) return DFSPH_B200_ERR_CUDA;
+    c->cap = cap;
+    return 0;
+}
+
+// AoS Real[3] <-> Real4 conversions through the device staging buffer
+__global__ void k_unpack3(const Real* __restrict__ src, Real4* __restrict__ dst, unsigned n, const unsigned* __restrict__ id, int keep_w)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned s = id ? id[i] : i;
+    Real4 v = make_real4(src[3 * (size_t)s], src[3 * (size_t)s + 1], src[3 * (size_t)s + 2], (Real)0.0);
+    if (keep_w) v.w = dst[i].w;
+    st_real4(dst + i, v);
+}
+__global__ void k_pack3(const Real4* __restrict__ src, Real* __restrict__ dst, unsigned n, const unsigned* __restrict__ id)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned d = id ? id[i] : i;
+    const Real4 v = ld_gather(src + i);
+    dst[3 * (size_t)d] = v.x; dst[3 * (size_t)d + 1] = v.y; dst[3 * (size_t)d + 2] = v.z;
+}
+template <typename T>
+__global__ void k_pack1(const T* __restrict__ src, T* __restrict__ dst, unsigned n, const unsigned* __restrict__ id)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[id ? id[i] : i] = src[i];
+}
+template <typename T>
+__global__ void k_unpack1(const T* __restrict__ src, T* __restrict__ dst, unsigned n, const unsigned* __restrict__ id)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[i] = src[id ? id[i] : i];
+}
+__global__ void k_pack_w(const Real4* __restrict__ src, Real* __restrict__ dst, unsigned n, const unsigned* __restrict__ id)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[id ? id[i] : i] = src[i].w;
+}
+
+extern "C" {
+
+int dfsph_b200_set_fluid(dfsph_b200_ctx* c, uint64_t n64, const void* x_, const void* v_, const uint32_t* id, const uint32_t* state,
+                         double density0, double volume)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (n64 > 0 && !x_) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "x is NULL");
+    if (n64 > 0xfffffff0ull) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "too many particles for 32-bit indices");
+    if (!(density0 > 0.0) || !(volume > 0.0)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "density0 and volume must be > 0");
+    const unsigned n = (unsigned)n64;
+    unsigned cap = (unsigned)std::max<uint64_t>(std::max<uint64_t>(c->cfg.max_fluid_particles, n), 1);
+    if (cap > c->cap) { int rc = alloc_fluid(c, cap); if (rc) return rc; }
+    c->n = n;
+    c->density0 = density0;
+    c->volume = volume;
+    { int rc = setup_constants(c); if (rc) return rc; }
+    const Real* x = (const Real*)x_;
+    const Real* v = (const Real*)v_;
+    std::vector<Real4> hp(n), hv(n);
+    std::vector<unsigned> hid(n), hst(n);
+    for (unsigned i = 0; i < n; ++i) {
+        hp[i] = make_real4(x[3 * i], x[3 * i + 1], x[3 * i + 2], (Real)0.0);
+        hv[i] = v ? make_real4(v[3 * i], v[3 * i + 1], v[3 * i + 2], (Real)0.0) : make_real4(0, 0, 0, 0);
+        hid[i] = id ? id[i] : i;
+        hst[i] = state ? state[i] : 0u;
+    }
+    c->cur = 0; c->cur_pos = 0;
+    if (n > 0) {
+        CUDA_TRY(c, cudaMemcpy(c->pos[0], hp.data(), (size_t)n * sizeof(Real4), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->vel[0], hv.data(), (size_t)n * sizeof(Real4), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->id[0], hid.data(), (size_t)n * sizeof(unsigned), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->state[0], hst.data(), (size_t)n * sizeof(unsigned), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemset(c->kappa[0], 0, (size_t)n * sizeof(Real)));
+        CUDA_TRY(c, cudaMemset(c->kappa_v[0], 0, (size_t)n * sizeof(Real)));
+        CUDA_TRY(c, cudaMemset(c->density, 0, (size_t)n * sizeof(Real)));
+        CUDA_TRY(c, cudaMemset(c->factor, 0, (size_t)n * sizeof(Real)));
+        CUDA_TRY(c, cudaMemset(c->density_adv, 0, (size_t)n * sizeof(Real)));
+        CUDA_TRY(c, cudaMemset(c->acc, 0, (size_t)n * sizeof(Real4)));
+        CUDA_TRY(c, cudaMemset(c->nnbr, 0, (size_t)n * sizeof(unsigned)));
+        bbox_extend(c, x, n);
+    }
+    // time step size / time live on the device
+    Ctrl hc;
+    memset(&hc, 0, sizeof(hc));
+    hc.h = (Real)c->par.time_step_size;
+    hc.h_step = hc.h;
+    CUDA_TRY(c, cudaMemcpy(c->ctrl, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+    c->grid_valid = false;
+    c->tables_valid = false;
+    c->pred_iter = 2; c->pred_iter_v = 1;
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_add_boundary(dfsph_b200_ctx* c, uint64_t n, const void* x_, const void* V_, int is_dynamic)
+{
+    CHECK_CTX(c);
+    if (is_dynamic) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "dynamic / animated rigid bodies are outside the hot-path scope (static Akinci2012 boundaries only)");
+    if (n > 0 && !x_) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "x is NULL");
+    if (c->h_bpos.size() + n > 0xfffffff0ull) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "too many boundary particles");
+    const Real* x = (const Real*)x_;
+    const Real* V = (const Real*)V_;
+    if (!V) c->have_bvol = false;
+    for (uint64_t i = 0; i < n; ++i) c->h_bpos.push_back(make_real4(x[3 * i], x[3 * i + 1], x[3 * i + 2], V ? V[i] : (Real)0.0));
+    bbox_extend(c, x, n);
+    c->boundary_dirty = true;
+    c->grid_valid = false;
+    c->tables_valid = false;
+    return DFSPH_B200_OK;
+}
+
+static int prepare(dfsph_b200_ctx* c)
+{
+    cudaSetDevice(c->cfg.device);
+    if (c->cap == 0) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "set_fluid has not been called");
+    if (!c->grid_valid) { int rc = setup_grid(c); if (rc) return rc; }
+    if (c->boundary_dirty) { int rc = finalize_boundary(c); if (rc) return rc; }
+    return 0;
+}
+
+int dfsph_b200_compute_boundary_volume(dfsph_b200_ctx* c)
+{
+    CHECK_CTX(c);
+    if (c->volume <= 0.0) {   // constants need the support radius only; allow calling before set_fluid
+        c->volume = 1.0;
+        int rc0 = setup_constants(c); c->volume = 0.0; if (rc0) return rc0;
+    }
+    if (c->cap == 0) { int rc = alloc_fluid(c, (unsigned)std::max<uint64_t>(c->cfg.max_fluid_particles, 1)); if (rc) return rc; }
+    int rc = prepare(c);
+    if (rc) return rc;
+    const unsigned nb = c->nb;
+    if (nb == 0) { c->have_bvol = true; return DFSPH_B200_OK; }
+    Real* vol = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&vol, (size_t)nb * sizeof(Real)));
+    const Real W0 = c->sph_bv.W_zero;   // sim->W_zero() (BoundaryModel_Akinci2012.cpp:61)
+    if (c->bv_mode == KM_LUT) k_boundary_volume<KM_LUT><<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->grid, c->sph_bv, W0, c->bpos, c->bcell_start, vol);
+    else k_boundary_volume<KM_CUBIC><<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->grid, c->sph_bv, W0, c->bpos, c->bcell_start, vol);
+    k_set_w<<<div_up(nb, 256), 256, 0, c->stream>>>(c->bpos, vol, nb);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    // keep the host copy in sync (the boundary may be re-sorted if the grid changes)
+    std::vector<Real> hv(nb);
+    std::vector<unsigned> ho(nb);
+    if (e == cudaSuccess) e = cudaMemcpy(hv.data(), vol, (size_t)nb * sizeof(Real), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ho.data(), c->borig, (size_t)nb * sizeof(unsigned), cudaMemcpyDeviceToHost);
+    cudaFree(vol);
+    if (e != cudaSuccess) { c->sticky = 1; CTX_FAIL(c, DFSPH_B200_ERR_CUDA, "boundary volume: %s", cudaGetErrorString(e)); }
+    for (unsigned i = 0; i < nb; ++i) c->h_bpos[ho[i]].w = hv[i];
+    c->have_bvol = true;
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_set_params(dfsph_b200_ctx* c, const dfsph_b200_params* p)
+{
+    CHECK_CTX(c);
+    if (!p) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "null params");
+    dfsph_b200_params q = *p;
+    // GenParam min-value clamps of the reference (TimeStepDFSPH.cpp:86-109)
+    if (q.max_iterations < 1) q.max_iterations = 1;
+    if (q.max_iterations_v < 1) q.max_iterations_v = 1;
+    if (q.max_error < 1e-6) q.max_error = 1e-6;
+    if (q.max_error_v < 1e-6) q.max_error_v = 1e-6;
+    if (!(q.time_step_size > 0.0)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "time_step_size must be > 0");
+    if (q.cfl_method < 0 || q.cfl_method > 2) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "cfl_method must be 0, 1 or 2");
+    const bool h_changed = (q.time_step_size != c->par.time_step_size);
+    c->par = q;
+    if (h_changed && c->ctrl) {
+        cudaSetDevice(c->cfg.device);
+        const Real h = (Real)q.time_step_size;
+        CUDA_TRY(c, cudaMemcpy(&c->ctrl->h, &h, sizeof(Real), cudaMemcpyHostToDevice));
+    }
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_get_params(const dfsph_b200_ctx* c, dfsph_b200_params* p)
+{
+    if (!c || !p) return DFSPH_B200_ERR_INVALID;
+    *p = c->par;
+    return DFSPH_B200_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+static FluidArrays fluid_arrays(dfsph_b200_ctx* c)
+{
+    FluidArrays f;
+    f.pos = c->pos[c->cur_pos];
+    f.vel = c->vel[c->cur];
+    f.acc = c->acc; f.bgrad = c->bgrad;
+    f.density = c->density; f.factor = c->factor; f.density_adv = c->density_adv;
+    f.kappa = c->kappa[c->cur]; f.kappa_v = c->kappa_v[c->cur];
+    f.state = c->state[c->cur]; f.nnbr = c->nnbr;
+    f.tab_f = c->tab_f; f.cnt_f = c->cnt_f; f.tab_b = c->tab_b; f.cnt_b = c->cnt_b;
+    f.Kf = c->Kf; f.Kb = c->Kb; f.n = c->n;
+    return f;
+}
+
+// Simulation::performNeighborhoodSearch: sort + reorder + neighbour table
+static int run_search(dfsph_b200_ctx* c)
+{
+    const unsigned n = c->n;
+    cudaStream_t st = c->stream;
+    int rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start);
+    if (rc) return rc;
+    if (n > 0) {
+        const int src = c->cur, dst = 1 - c->cur;
+        const int psrc = c->cur_pos, pdst = 1 - c->cur_pos;
+        k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
+            c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst]);
+        c->cur = dst; c->cur_pos = pdst;
+        k_build_neighbors<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
+            c->bpos, c->bcell_start, c->nb, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->ctrl);
+        c->launches += 2;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    c->tables_valid = true;
+    return 0;
+}
+
+template <int MODE>
+static int run_solver(dfsph_b200_ctx* c)
+{
+    const unsigned n = c->n;
+    cudaStream_t st = c->stream;
+    const unsigned grid = std::max(div_up(n, DFSPH_BLOCK), 1u);
+    const SolverParams sp = make_solver_params(c);
+    const bool div = c->par.enable_divergence_solver != 0;
+    FluidArrays f = fluid_arrays(c);
+
+    if (div) k_init_sweep<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl);
+    else k_init_sweep<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl);
+    c->launches++;
+
+    auto solve_loop = [&](int solve, unsigned max_it, unsigned& pred) -> int {
+        k_solve_begin<<<1, 1, 0, st>>>(c->ctrl, solve);
+        c->launches++;
+        unsigned launched = 0;
+        unsigned batch = std::min(std::max(pred + 1u, 2u), max_it);
+        while (true) {
+            for (unsigned b = 0; b < batch; ++b) {
+                k_accel<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl);
+                if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial);
+                else k_jacobi<MODE, SOLVE_PRESS><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial);
+                c->launches += 2;
+            }
+            launched += batch;
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+            if (c->h_ctrl->done || launched >= max_it) break;
+            batch = std::min(2u, max_it - launched);
+        }
+        pred = c->h_ctrl->iter;
+        return 0;
+    };
+
+    if (div) {
+        // the reference's iteration is a no-op for an empty model: avg stays 0, one iteration is counted
+        int rc = solve_loop(SOLVE_DIV, c->par.max_iterations_v, c->pred_iter_v);
+        if (rc) return rc;
+        k_div_final<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
+    } else {
+        k_div_final<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
+    }
+    k_update_time_step<<<1, 1, 0, st>>>(c->ctrl, sp);
+    k_press_init<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl);
+    c->launches += 3;
+    {
+        int rc = solve_loop(SOLVE_PRESS, c->par.max_iterations, c->pred_iter);
+        if (rc) return rc;
+    }
+    Real4* pos_out = c->pos[1 - c->cur_pos];
+    k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out);
+    k_step_end<<<1, 1, 0, st>>>(c->ctrl);
+    c->launches += 2;
+    c->cur_pos = 1 - c->cur_pos;
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
+{
+    int rc = prepare(c);
+    if (rc) return rc;
+    if (c->nb > 0 && !c->have_bvol) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "boundary volumes missing: pass V to add_boundary or call compute_boundary_volume");
+    c->launches = 0;
+    cudaStream_t st = c->stream;
+    // divergence solver disabled -> iterationsV = 0 (TimeStepDFSPH.cpp:170)
+    CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+    k_step_begin<<<1, 1, 0, st>>>(c->ctrl);
+    c->launches++;
+    if (!c->tables_valid) { rc = run_search(c); if (rc) return rc; }
+    CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
+#if DFSPH_REAL_IS_DOUBLE
+    if (c->solver_mode == KM_CUBIC) rc = run_solver<KM_CUBIC>(c);
+    else rc = run_solver<KM_LUT>(c);
+#else
+    rc = run_solver<KM_CUBIC_AVX>(c);
+#endif
+    if (rc) return rc;
+    c->tables_valid = false;   // positions advanced; table describes the pre-advection positions (as in the reference)
+    CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
+    if (stats) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        const Ctrl& hc = *c->h_ctrl;
+        memset(stats, 0, sizeof(*stats));
+        stats->iterations = hc.iterations;
+        stats->iterations_v = c->par.enable_divergence_solver ? hc.iterations_v : 0u;
+        stats->avg_density_error = hc.avg_err;
+        stats->avg_density_error_v = hc.avg_err_v;
+        stats->time_step_size = (double)hc.h;
+        stats->time = hc.time;
+        stats->num_particles = c->n;
+        stats->max_neighbors = hc.max_nbr;
+        stats->gpu_launches = c->launches;
+        cudaEventElapsedTime(&stats->ms_search, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&stats->ms_solver, c->ev[1], c->ev[2]);
+        if (hc.overflow > c->Kf || hc.overflow_b > c->Kb) {
+            CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "neighbour table capacity exceeded: need %u fluid / %u boundary slots (have %u / %u); raise max_*_neighbors",
+                     hc.overflow, hc.overflow_b, c->Kf, c->Kb);
+        }
+    }
+    return DFSPH_B200_OK;
+}
+
+extern "C" {
+
+int dfsph_b200_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
+{
+    CHECK_CTX(c);
+    return do_step(c, stats);
+}
+
+int dfsph_b200_search_and_density(dfsph_b200_ctx* c)
+{
+    CHECK_CTX(c);
+    int rc = prepare(c);
+    if (rc) return rc;
+    rc = run_search(c);
+    if (rc) return rc;
+    const unsigned grid = std::max(div_up(c->n, DFSPH_BLOCK), 1u);
+    FluidArrays f = fluid_arrays(c);
+    // density only: run the fused sweep without the divergence part (factor is a by-product)
+#if DFSPH_REAL_IS_DOUBLE
+    if (c->solver_mode == KM_CUBIC) k_init_sweep<KM_CUBIC, false><<<grid, DFSPH_BLOCK, 0, c->stream>>>(f, c->sph, c->bpos, c->ctrl);
+    else k_init_sweep<KM_LUT, false><<<grid, DFSPH_BLOCK, 0, c->stream>>>(f, c->sph, c->bpos, c->ctrl);
+#else
+    k_init_sweep<KM_CUBIC_AVX, false><<<grid, DFSPH_BLOCK, 0, c->stream>>>(f, c->sph, c->bpos, c->ctrl);
+#endif
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return DFSPH_B200_OK;
+}
+
+static size_t field_elem_bytes(dfsph_b200_field f)
+{
+    switch (f) {
+        case DFSPH_B200_FIELD_POSITION: case DFSPH_B200_FIELD_VELOCITY: case DFSPH_B200_FIELD_PRESSURE_ACCEL: return 3 * sizeof(Real);
+        case DFSPH_B200_FIELD_ID: case DFSPH_B200_FIELD_STATE: case DFSPH_B200_FIELD_NUM_NEIGHBORS: return sizeof(unsigned);
+        default: return sizeof(Real);
+    }
+}
+
+int dfsph_b200_download(dfsph_b200_ctx* c, dfsph_b200_field field, void* dst, size_t bytes, int by_id)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!dst) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "dst is NULL");
+    cudaStream_t st = c->stream;
+    if (field == DFSPH_B200_FIELD_BOUNDARY_VOLUME) {
+        if (bytes != c->h_bpos.size() * sizeof(Real)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "size mismatch for boundary volume");
+        Real* o = (Real*)dst;
+        for (size_t i = 0; i < c->h_bpos.size(); ++i) o[i] = c->h_bpos[i].w;
+        return DFSPH_B200_OK;
+    }
+    const unsigned n = c->n;
+    const size_t eb = field_elem_bytes(field);
+    if (bytes != (size_t)n * eb) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "size mismatch: field needs %zu bytes, got %zu", (size_t)n * eb, bytes);
+    if (n == 0) return DFSPH_B200_OK;
+    { int rc = ensure_stage(c, (size_t)n * eb); if (rc) return rc; }
+    const unsigned* idmap = by_id ? c->id[c->cur] : nullptr;
+    const unsigned g = div_up(n, 256);
+    switch (field) {
+        case DFSPH_B200_FIELD_POSITION: k_pack3<<<g, 256, 0, st>>>(c->pos[c->cur_pos], (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_VELOCITY: k_pack3<<<g, 256, 0, st>>>(c->vel[c->cur], (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_PRESSURE_ACCEL: k_pack3<<<g, 256, 0, st>>>(c->acc, (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_DENSITY: k_pack1<Real><<<g, 256, 0, st>>>(c->density, (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_FACTOR: k_pack1<Real><<<g, 256, 0, st>>>(c->factor, (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_DENSITY_ADV: k_pack1<Real><<<g, 256, 0, st>>>(c->density_adv, (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_KAPPA: k_pack1<Real><<<g, 256, 0, st>>>(c->kappa[c->cur], (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_KAPPA_V: k_pack1<Real><<<g, 256, 0, st>>>(c->kappa_v[c->cur], (Real*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_ID: k_pack1<unsigned><<<g, 256, 0, st>>>(c->id[c->cur], (unsigned*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_STATE: k_pack1<unsigned><<<g, 256, 0, st>>>(c->state[c->cur], (unsigned*)c->stage, n, idmap); break;
+        case DFSPH_B200_FIELD_NUM_NEIGHBORS: k_pack1<unsigned><<<g, 256, 0, st>>>(c->nnbr, (unsigned*)c->stage, n, idmap); break;
+        default: CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "unknown field %d", (int)field);
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(dst, c->stage, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_upload(dfsph_b200_ctx* c, dfsph_b200_field field, const void* src, size_t bytes, int by_id)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!src) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "src is NULL");
+    const unsigned n = c->n;
+    const size_t eb = field_elem_bytes(field);
+    if (bytes != (size_t)n * eb) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "size mismatch: field needs %zu bytes, got %zu", (size_t)n * eb, bytes);
+    if (n == 0) return DFSPH_B200_OK;
+    { int rc = ensure_stage(c, (size_t)n * eb); if (rc) return rc; }
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaMemcpyAsync(c->stage, src, bytes, cudaMemcpyHostToDevice, st));
+    const unsigned* idmap = by_id ? c->id[c->cur] : nullptr;
+    const unsigned g = div_up(n, 256);
+    switch (field) {
+        case DFSPH_B200_FIELD_POSITION: k_unpack3<<<g, 256, 0, st>>>((const Real*)c->stage, c->pos[c->cur_pos], n, idmap, 0); c->tables_valid = false; break;
+        case DFSPH_B200_FIELD_VELOCITY: k_unpack3<<<g, 256, 0, st>>>((const Real*)c->stage, c->vel[c->cur], n, idmap, 0); break;
+        case DFSPH_B200_FIELD_KAPPA: k_unpack1<Real><<<g, 256, 0, st>>>((const Real*)c->stage, c->kappa[c->cur], n, idmap); break;
+        case DFSPH_B200_FIELD_KAPPA_V: k_unpack1<Real><<<g, 256, 0, st>>>((const Real*)c->stage, c->kappa_v[c->cur], n, idmap); break;
+        case DFSPH_B200_FIELD_STATE: k_unpack1<unsigned><<<g, 256, 0, st>>>((const unsigned*)c->stage, c->state[c->cur], n, idmap); break;
+        default: CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "field %d is not uploadable (solver output)", (int)field);
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_step_host(dfsph_b200_ctx* c, void* x_inout, void* v_inout, void* density_out, dfsph_b200_step_stats* stats)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!x_inout || !v_inout) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "x/v buffers are NULL");
+    const unsigned n = c->n;
+    const size_t b3 = (size_t)n * 3 * sizeof(Real);
+    { int rc = ensure_stage(c, 2 * b3 + (size_t)n * sizeof(Real)); if (rc) return rc; }
+    cudaStream_t st = c->stream;
+    Real* sx = (Real*)c->stage;
+    Real* sv = sx + (size_t)n * 3;
+    Real* sd = sv + (size_t)n * 3;
+    const unsigned g = std::max(div_up(n, 256), 1u);
+    if (n > 0) {
+        CUDA_TRY(c, cudaMemcpyAsync(sx, x_inout, b3, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaMemcpyAsync(sv, v_inout, b3, cudaMemcpyHostToDevice, st));
+        k_unpack3<<<g, 256, 0, st>>>(sx, c->pos[c->cur_pos], n, c->id[c->cur], 0);
+        k_unpack3<<<g, 256, 0, st>>>(sv, c->vel[c->cur], n, c->id[c->cur], 0);
+    }
+    int rc = do_step(c, stats);
+    if (rc) return rc;
+    if (n > 0) {
+        k_pack3<<<g, 256, 0, st>>>(c->pos[c->cur_pos], sx, n, c->id[c->cur]);
+        k_pack3<<<g, 256, 0, st>>>(c->vel[c->cur], sv, n, c->id[c->cur]);
+        CUDA_TRY(c, cudaMemcpyAsync(x_inout, sx, b3, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(v_inout, sv, b3, cudaMemcpyDeviceToHost, st));
+        if (density_out) {
+            k_pack1<Real><<<g, 256, 0, st>>>(c->density, sd, n, c->id[c->cur]);
+            CUDA_TRY(c, cudaMemcpyAsync(density_out, sd, (size_t)n * sizeof(Real), cudaMemcpyDeviceToHost, st));
+        }
+        if (stats) stats->gpu_launches += density_out ? 5 : 4;
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return DFSPH_B200_OK;
+}
+
+}  // extern "C"
+
+// ---- neighbour export (tests / non-ported host code) ---------------------------------------------------------------
+__global__ void k_export_neighbors(unsigned n, const unsigned* __restrict__ tab, unsigned K, const unsigned* __restrict__ cnt,
+                                   const unsigned long long* __restrict__ offsets, const unsigned* __restrict__ remap, unsigned* __restrict__ out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned m = cnt[i];
+    const unsigned* t = tab + (size_t)(i >> 5) * K * DFSPH_TILE + (i & 31u);
+    unsigned* o = out + offsets[i];
+    for (unsigned k = 0; k < m; ++k) {   // insertion sort -> ascending lists
+        unsigned v = t[(size_t)k * DFSPH_TILE];
+        if (remap) v = remap[v];
+        unsigned b = k;
+        while (b > 0 && o[b - 1] > v) { o[b] = o[b - 1]; --b; }
+        o[b] = v;
+    }
+}
+
+extern "C" {
+
+int dfsph_b200_neighbors(dfsph_b200_ctx* c, int other, uint32_t* counts, uint64_t* offsets, uint32_t* idx, uint64_t cap)
+{
+    CHECK_CTX(c);
+    if (other != 0 && other != 1) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "other must be 0 (fluid) or 1 (boundary)");
+    if (!counts) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "counts is NULL");
+    int rc = prepare(c);
+    if (rc) return rc;
+    if (!c->tables_valid) { rc = run_search(c); if (rc) return rc; }
+    const unsigned n = c->n;
+    if (n == 0) { if (offsets) offsets[0] = 0; return DFSPH_B200_OK; }
+    const unsigned* cnt = other == 0 ? c->cnt_f : c->cnt_b;
+    CUDA_TRY(c, cudaMemcpyAsync(counts, cnt, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!idx) return DFSPH_B200_OK;
+    if (!offsets) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "offsets is NULL");
+    std::vector<unsigned long long> off(n + 1);
+    off[0] = 0;
+    for (unsigned i = 0; i < n; ++i) off[i + 1] = off[i] + counts[i];
+    for (unsigned i = 0; i <= n; ++i) offsets[i] = off[i];
+    if (off[n] > cap) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "idx capacity %llu < %llu entries", (unsigned long long)cap, off[n]);
+    if (off[n] == 0) return DFSPH_B200_OK;
+    unsigned long long* d_off = nullptr;
+    unsigned* d_out = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&d_off, (size_t)(n + 1) * sizeof(unsigned long long)));
+    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)off[n] * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off.data(), (size_t)(n + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        k_export_neighbors<<<div_up(n, 256), 256, 0, c->stream>>>(n, other == 0 ? c->tab_f : c->tab_b, other == 0 ? c->Kf : c->Kb, cnt, d_off,
+                                                                 other == 0 ? nullptr : c->borig, d_out);
+        e = cudaMemcpyAsync(idx, d_out, (size_t)off[n] * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_off);
+    if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) { c->sticky = 1; CTX_FAIL(c, DFSPH_B200_ERR_CUDA, "neighbors: %s", cudaGetErrorString(e)); }
+    return DFSPH_B200_OK;
+}
+
+}  // extern "C"
+
+// ---- kernel function evaluation (KernelTests.cpp on the device) -------------------------------------------------------
+template <int MODE>
+__global__ void k_eval_kernel(SphConst c, unsigned n, const Real* __restrict__ r, Real* __restrict__ W, Real* __restrict__ gW)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Real rx = r[3 * (size_t)i], ry = r[3 * (size_t)i + 1], rz = r[3 * (size_t)i + 2];
+    const Real r2 = rx * rx + ry * ry + rz * rz;
+    if (W) W[i] = sph_W<MODE>(c, r2);
+    if (gW) {
+        const Real g = sph_gradW_scale<MODE>(c, r2);
+        gW[3 * (size_t)i] = g * rx; gW[3 * (size_t)i + 1] = g * ry; gW[3 * (size_t)i + 2] = g * rz;
+    }
+}
+
+extern "C" {
+
+// kernel: 0 cubic (scalar arithmetic), 4 precomputed cubic, -1 = the solver's own kernel (CubicKernel_AVX in f32)
+int dfsph_b200_eval_kernel(dfsph_b200_ctx* c, int kernel, uint64_t n64, const void* r, void* W, void* gradW)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!r || (!W && !gradW)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "null argument");
+    if (c->lutW == nullptr) {
+        const double v = c->volume; if (v <= 0.0) c->volume = 1.0;
+        int rc = setup_constants(c); c->volume = v; if (rc) return rc;
+    }
+    int mode;
+    if (kernel == DFSPH_B200_KERNEL_CUBIC) mode = KM_CUBIC;
+    else if (kernel == DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC) mode = KM_LUT;
+    else if (kernel == -1) mode = c->solver_mode;
+    else CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "unsupported kernel id %d", kernel);
+    const unsigned n = (unsigned)n64;
+    if (n == 0) return DFSPH_B200_OK;
+    Real *dr = nullptr, *dW = nullptr, *dG = nullptr;
+    CUDA_TRY(c, cudaMalloc((void**)&dr, (size_t)n * 3 * sizeof(Real)));
+    cudaError_t e = cudaMalloc((void**)&dW, (size_t)n * sizeof(Real));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dG, (size_t)n * 3 * sizeof(Real));
+    if (e == cudaSuccess) e = cudaMemcpy(dr, r, (size_t)n * 3 * sizeof(Real), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const unsigned g = div_up(n, 256);
+        if (mode == KM_CUBIC_AVX) k_eval_kernel<KM_CUBIC_AVX><<<g, 256, 0, c->stream>>>(c->sph, n, dr, dW, dG);
+        else if (mode == KM_CUBIC) k_eval_kernel<KM_CUBIC><<<g, 256, 0, c->stream>>>(c->sph, n, dr, dW, dG);
+        else k_eval_kernel<KM_LUT><<<g, 256, 0, c->stream>>>(c->sph, n, dr, dW, dG);
+        e = cudaStreamSynchronize(c->stream);
+    }
+    if (e == cudaSuccess && W) e = cudaMemcpy(W, dW, (size_t)n * sizeof(Real), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && gradW) e = cudaMemcpy(gradW, dG, (size_t)n * 3 * sizeof(Real), cudaMemcpyDeviceToHost);
+    cudaFree(dr); if (dW) cudaFree(dW); if (dG) cudaFree(dG);
+    if (e != cudaSuccess) { c->sticky = 1; CTX_FAIL(c, DFSPH_B200_ERR_CUDA, "eval_kernel: %s", cudaGetErrorString(e)); }
+    return DFSPH_B200_OK;
+}
+
+// pinned host buffers for the host-buffer (e2e) path
+void* dfsph_b200_alloc_pinned(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void dfsph_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// device time of the whole stream so far: callers time with their own events through these
+int dfsph_b200_synchronize(dfsph_b200_ctx* c)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return DFSPH_B200_OK;
+}
+
+}  // extern "C"

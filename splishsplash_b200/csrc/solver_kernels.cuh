@@ -1,0 +1,492 @@
+// DFSPH solver kernels.  Every kernel is one thread per fluid particle ("writer owns particle
+// i", race-free by construction) sweeping that particle's neighbour table.  Per step:
+//   k_init_sweep      K1+K2+K3: computeDensities (TimeStep.cpp:54-169) + computeDFSPHFactor (TimeStepDFSPH.cpp:735-825 /
+//                     1106-1186) + computeDensityChange and the divergence warm start (:894-950 / 1247-1295, :410-461)
+//                     in ONE sweep -- all three depend only on x, v of the step start.  Also the only kernel that
+//                     touches boundary particles: it leaves G_i = sum_b V_b gradW_ib in `bgrad`, which is all later
+//                     kernels need of a static Akinci boundary.
+//   k_accel           pass A of an iteration: computePressureAccel (:954-1039 / 1299-1367)
+//   k_jacobi<DIV|PRESS>  pass B: compute_aij_pj + Jacobi update + density-error reduction + loop control
+//                     (:1042-1100 / 1370-1420, :576-612, :653-699, :324-341, :477-495), decided on the device.
+//   k_div_final       divergence finaliser (:500-539) + clearAccelerations (TimeStep.cpp:35-50) + CFL scan
+//                     (Simulation.cpp:415-493) + v += h a (TimeStepDFSPH.cpp:192-208)
+//   k_press_init      computeDensityAdv + pressure warm start (:830-889 / 1191-1242, :272-307)
+//   k_press_final     pressure finaliser (:351-382) + x += h v (:220-237)
+// Float build = semantics of the reference's AVX variant, double build = scalar variant.
+#pragma once
+#include "common.cuh"
+#include "sph_kernels.cuh"
+
+#define DFSPH_EPS ((Real)1.0e-5)   /* TimeStepDFSPH::m_eps, TimeStepDFSPH.h:28 */
+
+struct FluidArrays {
+    Real4* pos;          // (x, y, z, kappa of the running solve)
+    Real4* vel;          // (vx, vy, vz, -)
+    Real4* acc;          // pressure acceleration (ax, ay, az, -)
+    Real4* bgrad;        // G_i = sum_b V_b gradW(x_i - x_b)
+    Real* density;
+    Real* factor;
+    Real* density_adv;
+    Real* kappa;         // persistent warm-start value p/rho^2   (time-step independent form)
+    Real* kappa_v;       // persistent warm-start value p_v/rho^2
+    unsigned* state;
+    unsigned* nnbr;      // fluid + boundary neighbour count (particle-deficiency test)
+    const unsigned* tab_f;
+    const unsigned* cnt_f;
+    const unsigned* tab_b;
+    const unsigned* cnt_b;
+    unsigned Kf, Kb;
+    unsigned n;
+};
+
+__device__ __forceinline__ const unsigned* tab_ptr(const unsigned* tab, unsigned K, unsigned i)
+{
+    return tab + (size_t)(i >> 5) * K * DFSPH_TILE + (i & 31u);
+}
+
+// ---- block reduction helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_double(double v)
+{
+    __shared__ double ws[DFSPH_BLOCK / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) ws[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = lane < (DFSPH_BLOCK / 32) ? ws[lane] : 0.0;
+#pragma unroll
+        for (int d = 4; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+    }
+    return t;   // valid in thread 0
+}
+
+// true in every thread of the block that arrives last at the ticket (deterministic final reduction happens there)
+__device__ __forceinline__ bool last_block(Ctrl* ctrl)
+{
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&ctrl->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) ctrl->ticket = 0;
+    }
+    __syncthreads();
+    return is_last;
+}
+
+// ---- K1+K2+K3 ------------------------------------------------------------------------------------------------------
+template <int MODE, bool DIV_SOLVER>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphConst c, const Real4* __restrict__ bpos, Ctrl* ctrl)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    const Real4 xi = ld_plain(f.pos + i);   // plain loads: this kernel writes pos.w
+    const Real4 vi = ld_gather(f.vel + i);
+    const Real V = c.V;
+
+    Real dens = (Real)0.0;
+    Real gx = (Real)0.0, gy = (Real)0.0, gz = (Real)0.0;   // sum_j V gradW_ij (fluid)
+    Real sum_grad2 = (Real)0.0;
+    Real dadv = (Real)0.0;
+
+    const unsigned nf = f.cnt_f[i];
+    const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
+#pragma unroll 2
+    for (unsigned k = 0; k < nf; ++k) {
+        const unsigned j = tf[(size_t)k * DFSPH_TILE];
+        const Real4 xj = ld_plain(f.pos + j);
+        const Real4 vj = ld_gather(f.vel + j);
+        const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        Real W, g;
+        sph_W_gradW<MODE>(c, r2, W, g);
+        dens += V * W;
+#if DFSPH_REAL_IS_DOUBLE
+        // scalar variant: grad_p_j = -V gradW; sum += |grad_p_j|^2; grad_p_i -= grad_p_j; dadv sums without V
+        const Real px = V * (g * rx), py = V * (g * ry), pz = V * (g * rz);
+        sum_grad2 += px * px + py * py + pz * pz;
+        gx += px; gy += py; gz += pz;
+        dadv += (vi.x - vj.x) * (g * rx) + (vi.y - vj.y) * (g * ry) + (vi.z - vj.z) * (g * rz);
+#else
+        // AVX variant: V_gradW = gradW * V_j
+        const Real px = (rx * g) * V, py = (ry * g) * V, pz = (rz * g) * V;
+        sum_grad2 += px * px + py * py + pz * pz;
+        gx += px; gy += py; gz += pz;
+        dadv += (vi.x - vj.x) * px + (vi.y - vj.y) * py + (vi.z - vj.z) * pz;
+#endif
+    }
+#if DFSPH_REAL_IS_DOUBLE
+    dadv *= V;   // "assumes that all fluid particles have the same volume" (TimeStepDFSPH.cpp:1266-1267)
+#endif
+
+    // Akinci2012 boundary neighbours (static bodies: v_b = 0)
+    Real bx = (Real)0.0, by = (Real)0.0, bz = (Real)0.0;
+    const unsigned nb = f.cnt_b[i];
+    const unsigned* tb = tab_ptr(f.tab_b, f.Kb, i);
+    for (unsigned k = 0; k < nb; ++k) {
+        const unsigned j = tb[(size_t)k * DFSPH_TILE];
+        const Real4 xb = ld_gather(bpos + j);   // w = V_b
+        const Real rx = xi.x - xb.x, ry = xi.y - xb.y, rz = xi.z - xb.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        Real W, g;
+        sph_W_gradW<MODE>(c, r2, W, g);
+        dens += xb.w * W;
+        const Real px = xb.w * (g * rx), py = xb.w * (g * ry), pz = xb.w * (g * rz);
+        bx += px; by += py; bz += pz;
+        dadv += vi.x * px + vi.y * py + vi.z * pz;
+    }
+
+    // density (TimeStep.cpp:70,110 / 133,166)
+    const Real density = (V * c.W_zero + dens) * c.density0;
+    f.density[i] = density;
+    st_real4(f.bgrad + i, make_real4(bx, by, bz, (Real)0.0));
+
+    // factor (TimeStepDFSPH.cpp:812-821 / 1170-1182)
+    gx += bx; gy += by; gz += bz;
+    sum_grad2 += gx * gx + gy * gy + gz * gz;
+    Real factor = sum_grad2 > DFSPH_EPS ? (Real)1.0 / sum_grad2 : (Real)0.0;
+
+    const unsigned nn = nf + nb;
+    f.nnbr[i] = nn;
+
+    if (DIV_SOLVER) {
+        // divergence-solve init loop (TimeStepDFSPH.cpp:410-461)
+        const Real h = ctrl->h;
+        const Real invH = (Real)1.0 / h;
+        f.density_adv[i] = dadv;
+        Real dp = real_max(dadv, (Real)0.0);
+        if (nn < 20u) dp = (Real)0.0;
+        factor *= invH;
+        const Real kv_old = f.kappa_v[i];
+        const Real kv = dp > (Real)0.0 ? (Real)0.5 * real_min(kv_old, (Real)0.5) * invH : (Real)0.0;
+        f.pos[i].w = kv;
+    }
+    f.factor[i] = factor;
+}
+
+// ---- pressure acceleration of particle i from the kappa values in pos.w -------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphConst& c, unsigned i, const Real4 xi, Real& ax, Real& ay, Real& az)
+{
+    const Real ki = xi.w;
+    const Real V = c.V;
+    ax = ay = az = (Real)0.0;
+    const unsigned nf = f.cnt_f[i];
+    const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
+#pragma unroll 4
+    for (unsigned k = 0; k < nf; ++k) {
+        const unsigned j = tf[(size_t)k * DFSPH_TILE];
+        const Real4 xj = ld_plain(f.pos + j);
+        const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        const Real g = sph_gradW_scale<MODE>(c, r2);
+        const Real pSum = ki + xj.w;   // density0 ratio is 1 (single phase)
+#if DFSPH_REAL_IS_DOUBLE
+        if (real_abs(pSum) > DFSPH_EPS) {   // scalar variant skips tiny sums (TimeStepDFSPH.cpp:1323-1327)
+            const Real s = -V * g * pSum;
+            ax += s * rx; ay += s * ry; az += s * rz;
+        }
+#else
+        const Real s = (g * V) * pSum;      // delta_ai -= V_gradW * pSum (TimeStepDFSPH.cpp:987)
+        ax -= s * rx; ay -= s * ry; az -= s * rz;
+#endif
+    }
+    if (real_abs(ki) > DFSPH_EPS) {          // boundary term (:993-1010 / 1333-1345): a_i -= kappa_i * G_i
+        const Real4 b = ld_gather(f.bgrad + i);
+        ax -= ki * b.x; ay -= ki * b.y; az -= ki * b.z;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_accel(FluidArrays f, SphConst c, const Ctrl* __restrict__ ctrl)
+{
+    if (ctrl->done) return;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    Real ax = (Real)0.0, ay = (Real)0.0, az = (Real)0.0;
+    if (f.state[i] == 0u) {
+        const Real4 xi = ld_plain(f.pos + i);
+        pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+    }
+    st_real4(f.acc + i, make_real4(ax, ay, az, (Real)0.0));
+}
+
+// ---- pass B --------------------------------------------------------------------------------------------------------
+enum { SOLVE_DIV = 0, SOLVE_PRESS = 1 };
+
+template <int MODE, int SOLVE>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial)
+{
+    if (ctrl->done) return;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    double err = 0.0;
+    if (i < f.n && (SOLVE == SOLVE_DIV || f.state[i] == 0u)) {
+        const Real h = ctrl->h;
+        const Real4 xi = ld_plain(f.pos + i);
+        const Real4 ai = ld_gather(f.acc + i);
+        const Real V = c.V;
+        Real sum = (Real)0.0;
+        const unsigned nf = f.cnt_f[i];
+        const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
+#pragma unroll 4
+        for (unsigned k = 0; k < nf; ++k) {
+            const unsigned j = tf[(size_t)k * DFSPH_TILE];
+            const Real4 xj = ld_plain(f.pos + j);
+            const Real4 aj = ld_gather(f.acc + j);
+            const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+            const Real r2 = rx * rx + ry * ry + rz * rz;
+            const Real g = sph_gradW_scale<MODE>(c, r2);
+#if DFSPH_REAL_IS_DOUBLE
+            sum += (ai.x - aj.x) * (g * rx) + (ai.y - aj.y) * (g * ry) + (ai.z - aj.z) * (g * rz);
+#else
+            const Real s = g * V;
+            sum += (ai.x - aj.x) * (rx * s) + (ai.y - aj.y) * (ry * s) + (ai.z - aj.z) * (rz * s);
+#endif
+        }
+#if DFSPH_REAL_IS_DOUBLE
+        sum *= V;
+#endif
+        const Real4 b = ld_gather(f.bgrad + i);
+        sum += ai.x * b.x + ai.y * b.y + ai.z * b.z;
+
+        Real aij_pj = sum;
+        Real s_i;
+        if (SOLVE == SOLVE_PRESS) { aij_pj *= h * h; s_i = (Real)1.0 - f.density_adv[i]; }
+        else { aij_pj *= h; s_i = -f.density_adv[i]; }
+        Real residuum = real_min(s_i - aij_pj, (Real)0.0);
+        if (SOLVE == SOLVE_DIV && f.nnbr[i] < 20u) residuum = (Real)0.0;
+        const Real knew = real_max(xi.w - (Real)0.5 * (s_i - aij_pj) * f.factor[i], (Real)0.0);
+        f.pos[i].w = knew;
+        err = -(double)(c.density0 * residuum);
+    }
+    // density-error reduction: block partials, summed in fixed order by the last block (deterministic)
+    const double bsum = block_sum_double(err);
+    if (threadIdx.x == 0) partial[blockIdx.x] = bsum;
+    if (last_block(ctrl)) {
+        double t = 0.0;
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += partial[b];
+        t = block_sum_double(t);
+        if (threadIdx.x == 0) {
+            // loop control (TimeStepDFSPH.cpp:324-341 / 477-495)
+            const Real density_error = (Real)t;
+            const Real avg = density_error / (Real)f.n;
+            Real eta;
+            unsigned min_it, max_it;
+            if (SOLVE == SOLVE_PRESS) { eta = sp.max_error * (Real)0.01 * c.density0; min_it = sp.min_iter; max_it = sp.max_iter; }
+            else { eta = ((Real)1.0 / ctrl->h) * sp.max_error_v * (Real)0.01 * c.density0; min_it = 1u; max_it = sp.max_iter_v; }
+            const bool chk = avg <= eta;
+            const unsigned it = ctrl->iter + 1u;
+            ctrl->iter = it;
+            if (SOLVE == SOLVE_PRESS) { ctrl->avg_err = (double)avg; ctrl->iterations = it; }
+            else { ctrl->avg_err_v = (double)avg; ctrl->iterations_v = it; }
+            const bool cont = (!chk || (it < min_it)) && (it < max_it);
+            ctrl->done = cont ? 0 : 1;
+        }
+    }
+}
+
+// Start of a solve: reset the loop state.  For n == 0 the reference's iteration returns immediately with avg = 0.
+__global__ void k_solve_begin(Ctrl* ctrl, int solve)
+{
+    ctrl->iter = 0;
+    ctrl->done = 0;
+    ctrl->ticket = 0;
+    if (solve == SOLVE_PRESS) { ctrl->iterations = 0; ctrl->avg_err = 0.0; }
+    else { ctrl->iterations_v = 0; ctrl->avg_err_v = 0.0; }
+}
+
+// ---- divergence finaliser + non-pressure kick + CFL -----------------------------------------------------------------
+template <int MODE, bool DIV_SOLVER>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_div_final(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const Real h = ctrl->h;    // still the step's initial h here
+    Real velmag = (Real)0.0;
+    if (i < f.n) {
+        Real4 v = ld_gather(f.vel + i);
+        const unsigned st = f.state[i];
+        if (DIV_SOLVER) {
+            const Real4 xi = ld_plain(f.pos + i);
+            Real ax = (Real)0.0, ay = (Real)0.0, az = (Real)0.0;
+            if (st == 0u) pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+            st_real4(f.acc + i, make_real4(ax, ay, az, (Real)0.0));
+            v.x += h * ax; v.y += h * ay; v.z += h * az;                 // TimeStepDFSPH.cpp:516
+            f.factor[i] *= h;                                            // :518
+            f.kappa_v[i] = xi.w * h;                                     // :536
+        }
+        // clearAccelerations: a = g (TimeStep.cpp:41-48); CFL term |v + a h|^2 (Simulation.cpp:431-439)
+        const Real tx = v.x + sp.gx * h, ty = v.y + sp.gy * h, tz = v.z + sp.gz * h;
+        velmag = tx * tx + ty * ty + tz * tz;
+        if (st == 0u) { v.x += h * sp.gx; v.y += h * sp.gy; v.z += h * sp.gz; }   // TimeStepDFSPH.cpp:192-208
+        st_real4(f.vel + i, v);
+    }
+    // block max -> global max (non-negative floats order like their bit patterns)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) velmag = real_max(velmag, __shfl_xor_sync(0xffffffffu, velmag, d));
+    __shared__ Real wm[DFSPH_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = velmag;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Real m = wm[0];
+        for (int w = 1; w < DFSPH_BLOCK / 32; ++w) m = real_max(m, wm[w]);
+#if DFSPH_REAL_IS_DOUBLE
+        atomicMax(&ctrl->maxvel_bits, (unsigned long long)__double_as_longlong(m));
+#else
+        atomicMax(&ctrl->maxvel_bits, (unsigned long long)__float_as_uint(m));
+#endif
+    }
+}
+
+// Simulation::updateTimeStepSize (Simulation.cpp:395-413, 415-493) on the reduced maximum; one thread.
+__global__ void k_update_time_step(Ctrl* ctrl, SolverParams sp)
+{
+    Real h = ctrl->h;
+    ctrl->h_step = h;
+    if (sp.cfl_method == 1 || sp.cfl_method == 2) {
+#if DFSPH_REAL_IS_DOUBLE
+        Real maxVel = __longlong_as_double((long long)ctrl->maxvel_bits);
+#else
+        Real maxVel = __uint_as_float((unsigned)ctrl->maxvel_bits);
+#endif
+        const Real diameter = (Real)2.0 * sp.radius;
+        if (maxVel < (Real)1.0e-9) maxVel = (Real)1.0e-9;
+        Real hn = sp.cfl_factor * (Real)0.4 * (diameter / real_sqrt(maxVel));
+        hn = real_min(hn, sp.cfl_max);
+        hn = real_max(hn, sp.cfl_min);
+        if (sp.cfl_method == 2) {
+            // iteration-count based adaption (Simulation.cpp:399-412); iterations of the previous pressure solve
+            const unsigned iterations = ctrl->iterations;
+            if (iterations != 0u) {
+                Real h2 = h;
+                if (iterations > 10u) h2 *= (Real)0.9;
+                else if (iterations < 5u) h2 *= (Real)1.1;
+                hn = real_min(h2, hn);
+            }
+        }
+        h = hn;
+    }
+    ctrl->h = h;
+    ctrl->maxvel_bits = 0ull;
+}
+
+// ---- pressure solve init -------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_press_init(FluidArrays f, SphConst c, Ctrl* ctrl)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    const Real h = ctrl->h;     // the NEW time step size (TimeStepDFSPH.cpp:254)
+    const Real4 xi = ld_plain(f.pos + i);
+    const Real4 vi = ld_gather(f.vel + i);
+    const Real V = c.V;
+    Real delta = (Real)0.0;
+    const unsigned nf = f.cnt_f[i];
+    const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
+#pragma unroll 4
+    for (unsigned k = 0; k < nf; ++k) {
+        const unsigned j = tf[(size_t)k * DFSPH_TILE];
+        const Real4 xj = ld_plain(f.pos + j);
+        const Real4 vj = ld_gather(f.vel + j);
+        const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        const Real g = sph_gradW_scale<MODE>(c, r2);
+#if DFSPH_REAL_IS_DOUBLE
+        delta += (vi.x - vj.x) * (g * rx) + (vi.y - vj.y) * (g * ry) + (vi.z - vj.z) * (g * rz);
+#else
+        const Real s = g * V;
+        delta += (vi.x - vj.x) * (rx * s) + (vi.y - vj.y) * (ry * s) + (vi.z - vj.z) * (rz * s);
+#endif
+    }
+#if DFSPH_REAL_IS_DOUBLE
+    delta *= V;
+#endif
+    const Real4 b = ld_gather(f.bgrad + i);
+    delta += vi.x * b.x + vi.y * b.y + vi.z * b.z;
+
+    const Real dadv = f.density[i] / c.density0 + h * delta;     // :888 / 1241
+    f.density_adv[i] = dadv;
+    const Real invH2 = (Real)1.0 / (h * h);
+    f.factor[i] *= invH2;                                         // :283
+    const Real kold = f.kappa[i];
+    const Real k = dadv > (Real)1.0 ? (Real)0.5 * real_min(kold, (Real)0.00025) * invH2 : (Real)0.0;   // :291-294
+    f.pos[i].w = k;
+}
+
+// ---- pressure finaliser + advection ----------------------------------------------------------------------------------
+// Positions are written to pos_out (the other half of the double buffer): neighbours still read the old positions.
+template <int MODE>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_press_final(FluidArrays f, SphConst c, Ctrl* ctrl, Real4* __restrict__ pos_out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.n) return;
+    const Real h = ctrl->h;
+    const Real hs = ctrl->h_step;
+    const Real4 xi = ld_plain(f.pos + i);
+    const unsigned st = f.state[i];
+    Real ax = (Real)0.0, ay = (Real)0.0, az = (Real)0.0;
+    if (st == 0u) pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+    st_real4(f.acc + i, make_real4(ax, ay, az, (Real)0.0));
+    Real4 v = ld_gather(f.vel + i);
+    v.x += h * ax; v.y += h * ay; v.z += h * az;                  // :360
+    st_real4(f.vel + i, v);
+    f.kappa[i] = xi.w * (h * h);                                  // :379
+    Real4 xo = xi;
+    if (st == 0u) { xo.x += hs * v.x; xo.y += hs * v.y; xo.z += hs * v.z; }   // :220-237 (h captured at step start)
+    st_real4(pos_out + i, xo);
+}
+
+__global__ void k_step_begin(Ctrl* ctrl)
+{
+    ctrl->max_nbr = 0u;
+    ctrl->overflow = 0u;
+    ctrl->overflow_b = 0u;
+}
+
+__global__ void k_step_end(Ctrl* ctrl)
+{
+    ctrl->time += (double)ctrl->h_step;      // TimeStepDFSPH.cpp:248
+}
+
+// ---- Akinci2012 boundary volume (BoundaryModel_Akinci2012.cpp:48-75) -------------------------------------------------
+template <int W_MODE>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_boundary_volume(unsigned nb, GridDesc g, SphConst c, Real W_zero,
+    const Real4* __restrict__ bpos, const unsigned* __restrict__ bcell_start, Real* __restrict__ vol_out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const Real4 xi = ld_gather(bpos + i);
+    const int cx = cell_coord(xi.x, g.ox, g.inv_cell, g.nx);
+    const int cy = cell_coord(xi.y, g.oy, g.inv_cell, g.ny);
+    const int cz = cell_coord(xi.z, g.oz, g.inv_cell, g.nz);
+    Real delta = W_zero;
+    for (int dx = -1; dx <= 1; ++dx) {
+        const int x = cx + dx;
+        if (x < 0 || x >= g.nx) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = cy + dy;
+            if (y < 0 || y >= g.ny) continue;
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int z = cz + dz;
+                if (z < 0 || z >= g.nz) continue;
+                const unsigned key = cell_key(x, y, z, g);
+                const unsigned s = bcell_start[key], e = bcell_start[key + 1];
+                for (unsigned j = s; j < e; ++j) {
+                    if (j == i) continue;
+                    const Real4 xj = ld_gather(bpos + j);
+                    // neighbour predicate first (only list members contribute in the reference)
+                    const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+#if DFSPH_REAL_IS_DOUBLE
+                    double l2 = __dmul_rn(rx, rx); l2 = __dadd_rn(l2, __dmul_rn(ry, ry)); l2 = __dadd_rn(l2, __dmul_rn(rz, rz));
+#else
+                    float l2 = __fmul_rn(rx, rx); l2 = __fadd_rn(l2, __fmul_rn(ry, ry)); l2 = __fadd_rn(l2, __fmul_rn(rz, rz));
+#endif
+                    if (l2 < c.R2) delta += sph_W<W_MODE>(c, rx * rx + ry * ry + rz * rz);
+                }
+            }
+        }
+    }
+    vol_out[i] = (Real)1.0 / delta;
+}

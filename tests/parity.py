@@ -1,0 +1,150 @@
+"""Parity helpers shared by tests/, __graft_entry__.smoke() and tools/.  The oracle (oracle/_ref = the reference's own
+DFSPH sources, or the C++ restatement oracle/liboracle_*.so) is the CHECKER; the thing checked is the CUDA library
+reached through the C ABI (splishsplash_b200.solver.TimeStepDFSPH_B200).
+
+Tolerances (BASELINE.json north_star): fields within 1e-4 (float) / 1e-10 (double) relative error, neighbour sets
+bit-exact.  "Relative" is taken against the field's scale (max |reference| over the particles): element-wise
+relative error is meaningless for fields that cancel to ~0 in the bulk (pressure acceleration, velocity at rest),
+and the reference itself does not reproduce those element-wise when its neighbour order changes.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TOL = {"f32": 1.0e-4, "f64": 1.0e-10}
+
+STEP_FIELDS = ["density", "factor", "advected density", "p / rho^2", "p_v / rho^2", "velocity", "position",
+               "pressure acceleration"]
+
+
+def dtype_of(precision):
+    return np.float32 if precision == "f32" else np.float64
+
+
+def make_oracle(scene, precision, kernel=4, **params):
+    """Reference-side simulation: the reference's own sources if oracle/_ref is built, else the C++ restatement."""
+    from oracle import refsim
+    if refsim.ref_available(precision):
+        return refsim.build_ref_scene(scene, precision, kernel=kernel, **params), "reference"
+    from oracle import portsim
+    return portsim.build_port_scene(scene, precision, kernel=kernel, **params), "port"
+
+
+def scaled_err(a, b):
+    """max |a-b| / max |b|  (0 if both are identically zero)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = float(np.max(np.abs(b))) if b.size else 0.0
+    diff = float(np.max(np.abs(a - b))) if b.size else 0.0
+    if scale == 0.0:
+        return diff
+    return diff / scale
+
+
+def neighbor_sets_by_id(counts, offsets, idx, row_ids, col_ids=None):
+    """CSR in array order -> dict-free canonical form: (ids sorted, per-id sorted neighbour id arrays concatenated)."""
+    n = len(counts)
+    cols = idx if col_ids is None else col_ids[idx]
+    order = np.argsort(row_ids, kind="stable")
+    out_counts = counts[order]
+    out = np.empty(len(cols), dtype=np.uint32)
+    pos = 0
+    for r in order:
+        s, e = int(offsets[r]), int(offsets[r + 1])
+        seg = np.sort(cols[s:e])
+        out[pos:pos + (e - s)] = seg
+        pos += e - s
+    return out_counts, out
+
+
+def sync_state(ref, dev):
+    """Make the device start the next step from exactly the reference's current state."""
+    dev.set_field("position", ref.field_by_id("position"))
+    dev.set_field("velocity", ref.field_by_id("velocity"))
+    dev.set_field("p / rho^2", ref.field_by_id("p / rho^2"))
+    dev.set_field("p_v / rho^2", ref.field_by_id("p_v / rho^2"))
+    dev.setValue("timeStepSize", ref.h)
+
+
+def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, check_neighbors=True, **params):
+    """Run `steps` steps on the oracle and on the device from identical input states; compare every per-step field,
+    the iteration counts, the new time step size and (first step) the neighbour sets.  Returns a result dict."""
+    from splishsplash_b200.solver import build_b200_scene
+    tol = TOL[precision] if tol is None else tol
+    ref, kind = make_oracle(scene, precision, kernel=kernel, **params)
+    res = {"ok": True, "oracle": kind, "precision": precision, "steps": [], "max_err": {}}
+    try:
+        bx, bV = (None, None)
+        if scene.get("boundary_x") is not None and len(scene["boundary_x"]):
+            bx, bV = ref.boundary(0)
+        # boundary volumes: device-computed, checked against the reference's (then the reference's are used so that
+        # the step comparison starts from identical inputs)
+        dev = build_b200_scene(scene, precision, kernel=kernel, **params)
+        try:
+            if bx is not None:
+                # the reference z-sorts its boundary arrays once; match particles by position
+                key = lambda a: [tuple(r) for r in a.tolist()]
+                pos_to_V = dict(zip(key(bx), bV.tolist()))
+                refV = np.array([pos_to_V[k] for k in key(np.asarray(scene["boundary_x"], dtype=dtype_of(precision)))])
+                devV = dev.boundary_volume()
+                res["max_err"]["boundary volume"] = scaled_err(devV, refV)
+                if res["max_err"]["boundary volume"] > tol:
+                    res["ok"] = False
+            if check_neighbors:
+                ref.search_and_density()
+                rc, ro, ri = ref.neighbors(0, 0)
+                rid = ref.ids()
+                dc, do, di = dev.neighbors(0)
+                did = dev.field("id", by_id=False)
+                a = neighbor_sets_by_id(rc, ro, ri, rid, rid)
+                b = neighbor_sets_by_id(dc, do, di, did, did)
+                same = np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                res["neighbors_fluid_equal"] = bool(same)
+                res["neighbor_pairs"] = int(len(ri))
+                if bx is not None:
+                    rcb, rob, rib = ref.neighbors(0, 1)
+                    dcb, dob, dib = dev.neighbors(1)
+                    # map reference boundary array indices -> insertion indices via positions
+                    ins = {k: i for i, k in enumerate(key(np.asarray(scene["boundary_x"], dtype=dtype_of(precision))))}
+                    rmap = np.array([ins[k] for k in key(bx)], dtype=np.uint32)
+                    a = neighbor_sets_by_id(rcb, rob, rib, rid, rmap)
+                    b = neighbor_sets_by_id(dcb, dob, dib, did, None)
+                    sameb = np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                    res["neighbors_boundary_equal"] = bool(sameb)
+                    same = same and sameb
+                if not same:
+                    res["ok"] = False
+            for s in range(steps):
+                if resync or s == 0:
+                    sync_state(ref, dev)
+                ref.step(1)
+                st = dev.step(1)
+                rec = {"ref_iter": (ref.iterations_v, ref.iterations), "dev_iter": (int(st.iterations_v), int(st.iterations)),
+                       "ref_h": ref.h, "dev_h": float(st.time_step_size), "err": {}}
+                for name in STEP_FIELDS:
+                    e = scaled_err(dev.field(name), ref.field_by_id(name))
+                    rec["err"][name] = e
+                    res["max_err"][name] = max(res["max_err"].get(name, 0.0), e)
+                    if not (e <= tol):
+                        res["ok"] = False
+                if rec["ref_iter"] != rec["dev_iter"]:
+                    res["ok"] = False
+                if abs(rec["ref_h"] - rec["dev_h"]) > tol * abs(rec["ref_h"]):
+                    res["ok"] = False
+                res["steps"].append(rec)
+        finally:
+            dev.close()
+    finally:
+        ref.destroy()
+    worst = max(res["max_err"].items(), key=lambda kv: kv[1]) if res["max_err"] else ("-", 0.0)
+    res["summary"] = (f"oracle={kind} N={len(scene['fluid_x'])} steps={steps} worst={worst[0]}:{worst[1]:.3e} "
+                      f"iters={[(r['ref_iter'], r['dev_iter']) for r in res['steps']]} "
+                      f"nbr_equal={res.get('neighbors_fluid_equal')}/{res.get('neighbors_boundary_equal')} ok={res['ok']}")
+    return res
