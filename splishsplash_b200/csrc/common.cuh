@@ -136,3 +136,4 @@ struct SolverParams {
 
 #define DFSPH_BLOCK 256
 #define DFSPH_TILE 32
+#define DFSPH_PAD 4u     /* neighbour lists are padded to multiples of this (>= the sweep unroll factors) */

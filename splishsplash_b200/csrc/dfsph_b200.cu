@@ -41,7 +41,7 @@ struct dfsph_b200_ctx {
     int cur_pos = 0;    // buffer holding the current positions
     Real4 *acc = nullptr, *bgrad = nullptr;
     Real *density = nullptr, *factor = nullptr, *density_adv = nullptr;
-    unsigned *nnbr = nullptr, *cnt_f = nullptr, *cnt_b = nullptr, *tab_f = nullptr, *tab_b = nullptr;
+    unsigned *nnbr = nullptr, *cnt_f = nullptr, *cnt_b = nullptr, *tab_f = nullptr, *tab_b = nullptr, *tcnt_f = nullptr, *tcnt_b = nullptr;
     unsigned *cell_key = nullptr, *cell_rank = nullptr, *sorted_idx = nullptr;
     unsigned *cell_count = nullptr, *cell_start = nullptr, *scan_partial = nullptr;
     unsigned keys_cap = 0, scratch_cap = 0;
@@ -250,6 +250,8 @@ int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out)
     dfsph_b200_default_params(&c->par);
     c->Kf = cfg->max_fluid_neighbors > 0 ? (unsigned)cfg->max_fluid_neighbors : 64u;
     c->Kb = cfg->max_boundary_neighbors > 0 ? (unsigned)cfg->max_boundary_neighbors : 64u;
+    c->Kf = (c->Kf + DFSPH_PAD - 1u) & ~(DFSPH_PAD - 1u);
+    c->Kb = (c->Kb + DFSPH_PAD - 1u) & ~(DFSPH_PAD - 1u);
     int rc = 0;
     do {
         if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = -1; break; }
@@ -274,7 +276,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
         cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->kappa[k]); cudaFree(c->kappa_v[k]); cudaFree(c->id[k]); cudaFree(c->state[k]);
     }
     cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
-    cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b);
+    cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b); cudaFree(c->tcnt_f); cudaFree(c->tcnt_b);
     cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
     cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start);
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
@@ -399,7 +401,7 @@ static int finalize_boundary(dfsph_b200_ctx* c)
     if (!c->boundary_dirty) return 0;
     const unsigned nb = (unsigned)c->h_bpos.size();
     c->nb = nb;
-    const unsigned need = std::max(nb, 1u);
+    const unsigned need = nb + 1u;   // +1: sentinel boundary particle
     Real4* tmp = nullptr;
     unsigned* tmp_orig = nullptr;
     if (dev_alloc(c, &c->bpos, need)) return DFSPH_B200_ERR_CUDA;
@@ -428,14 +430,14 @@ static int finalize_boundary(dfsph_b200_ctx* c)
 static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
 {
     for (int k = 0; k < 2; ++k) {
-        if (dev_alloc(c, &c->pos[k], cap)) return DFSPH_B200_ERR_CUDA;
-        if (dev_alloc(c, &c->vel[k], cap)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->pos[k], cap + 1)) return DFSPH_B200_ERR_CUDA;   // +1: sentinel particle
+        if (dev_alloc(c, &c->vel[k], cap + 1)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->kappa[k], cap)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->kappa_v[k], cap)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->id[k], cap)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->state[k], cap)) return DFSPH_B200_ERR_CUDA;
     }
-    if (dev_alloc(c, &c->acc, cap)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->acc, cap + 1)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->bgrad, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->density, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->factor, cap)) return DFSPH_B200_ERR_CUDA;
@@ -447,6 +449,8 @@ static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
     c->ntiles_cap = ntiles;
     if (dev_alloc(c, &c->tab_f, (size_t)ntiles * c->Kf * DFSPH_TILE)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->tab_b, (size_t)ntiles * c->Kb * DFSPH_TILE)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->tcnt_f, ntiles)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->tcnt_b, ntiles)) return DFSPH_B200_ERR_CUDA;
     { int rs = ensure_scratch(c, cap); if (rs) return rs; }
     if (dev_alloc(c, &c->partial, div_up(cap, DFSPH_BLOCK) + 1)) return DFSPH_B200_ERR_CUDA;
     c->cap = cap;
@@ -644,7 +648,7 @@ static FluidArrays fluid_arrays(dfsph_b200_ctx* c)
     f.density = c->density; f.factor = c->factor; f.density_adv = c->density_adv;
     f.kappa = c->kappa[c->cur]; f.kappa_v = c->kappa_v[c->cur];
     f.state = c->state[c->cur]; f.nnbr = c->nnbr;
-    f.tab_f = c->tab_f; f.cnt_f = c->cnt_f; f.tab_b = c->tab_b; f.cnt_b = c->cnt_b;
+    f.tab_f = c->tab_f; f.cnt_f = c->cnt_f; f.tab_b = c->tab_b; f.cnt_b = c->cnt_b; f.tcnt_f = c->tcnt_f; f.tcnt_b = c->tcnt_b;
     f.Kf = c->Kf; f.Kb = c->Kb; f.n = c->n;
     return f;
 }
@@ -660,10 +664,10 @@ static int run_search(dfsph_b200_ctx* c)
         const int src = c->cur, dst = 1 - c->cur;
         const int psrc = c->cur_pos, pdst = 1 - c->cur_pos;
         k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
-            c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst]);
+            c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc);
         c->cur = dst; c->cur_pos = pdst;
         k_build_neighbors<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
-            c->bpos, c->bcell_start, c->nb, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->ctrl);
+            c->bpos, c->bcell_start, c->nb, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl);
         c->launches += 2;
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -147,10 +147,17 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_reorder(unsigned n, const unsig
     const Real4* __restrict__ pos_in, const Real4* __restrict__ vel_in, const Real* __restrict__ kappa_in, const Real* __restrict__ kappav_in,
     const unsigned* __restrict__ id_in, const unsigned* __restrict__ state_in,
     Real4* __restrict__ pos_out, Real4* __restrict__ vel_out, Real* __restrict__ kappa_out, Real* __restrict__ kappav_out,
-    unsigned* __restrict__ id_out, unsigned* __restrict__ state_out)
+    unsigned* __restrict__ id_out, unsigned* __restrict__ state_out, Real4* __restrict__ acc_sentinel)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (i == 0) {
+        // sentinel particle [n]: far away, at rest, no pressure -> contributes exactly 0 to every sum; the padded
+        // slots of the neighbour table point at it
+        st_real4(pos_out + n, make_real4((Real)1.0e15, (Real)1.0e15, (Real)1.0e15, (Real)0.0));
+        st_real4(vel_out + n, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+        st_real4(acc_sentinel + n, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+    }
     const unsigned s = sorted_idx[i];
     st_real4(pos_out + i, ld_gather(pos_in + s));
     st_real4(vel_out + i, ld_gather(vel_in + s));
@@ -166,6 +173,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_reorder_boundary(unsigned n, co
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (i == 0) st_real4(out + n, make_real4((Real)1.0e15, (Real)1.0e15, (Real)1.0e15, (Real)0.0));   // sentinel, V_b = 0
     const unsigned s = sorted_idx[i];
     st_real4(out + i, ld_gather(in + s));
     orig_out[i] = orig_in[s];
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_build_neighbors(unsigned n, Gri
     const Real4* __restrict__ pos, const unsigned* __restrict__ cell_start,
     const Real4* __restrict__ bpos, const unsigned* __restrict__ bcell_start, unsigned nb,
     unsigned* __restrict__ tab_f, unsigned Kf, unsigned* __restrict__ tab_b, unsigned Kb,
-    unsigned* __restrict__ cnt_f, unsigned* __restrict__ cnt_b, Ctrl* ctrl)
+    unsigned* __restrict__ cnt_f, unsigned* __restrict__ cnt_b, unsigned* __restrict__ tcnt_f, unsigned* __restrict__ tcnt_b, Ctrl* ctrl)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -238,13 +246,25 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_build_neighbors(unsigned n, Gri
     const unsigned cf = search_cells<true>(xi, i, g, R2, pos, cell_start, tab_f, Kf, tile, lane);
     unsigned cb = 0;
     if (nb > 0) cb = search_cells<false>(xi, i, g, R2, bpos, bcell_start, tab_b, Kb, tile, lane);
-    cnt_f[i] = cf < Kf ? cf : Kf;
-    cnt_b[i] = cb < Kb ? cb : Kb;
+    const unsigned sf = cf < Kf ? cf : Kf, sb = cb < Kb ? cb : Kb;
+    cnt_f[i] = sf;
+    cnt_b[i] = sb;
     if (cf > Kf) atomicMax(&ctrl->overflow, cf);
     if (cb > Kb) atomicMax(&ctrl->overflow_b, cb);
-    // statistics: largest fluid neighbour count
+    // pad every list of the warp tile with the sentinel index up to the tile maximum (rounded to DFSPH_PAD; Kf and
+    // Kb are multiples of DFSPH_PAD): the solver sweeps then run warp-uniform loops without tail handling
     const unsigned mask = __activemask();
-    const unsigned m = __reduce_max_sync(mask, cf);
-    if (lane == (unsigned)(__ffs(mask) - 1) && m > 0) atomicMax(&ctrl->max_nbr, m);
+    const unsigned mf = (__reduce_max_sync(mask, sf) + (DFSPH_PAD - 1u)) & ~(DFSPH_PAD - 1u);
+    const unsigned mb = (__reduce_max_sync(mask, sb) + (DFSPH_PAD - 1u)) & ~(DFSPH_PAD - 1u);
+    unsigned* pf = tab_f + (size_t)tile * Kf * DFSPH_TILE + lane;
+    for (unsigned k = sf; k < mf; ++k) pf[(size_t)k * DFSPH_TILE] = n;
+    unsigned* pb = tab_b + (size_t)tile * Kb * DFSPH_TILE + lane;
+    for (unsigned k = sb; k < mb; ++k) pb[(size_t)k * DFSPH_TILE] = nb;
+    if (lane == (unsigned)(__ffs(mask) - 1)) {
+        tcnt_f[tile] = mf;
+        tcnt_b[tile] = mb;
+    }
+    const unsigned mx = __reduce_max_sync(mask, cf);
+    if (lane == (unsigned)(__ffs(mask) - 1) && mx > 0) atomicMax(&ctrl->max_nbr, mx);
 }
 

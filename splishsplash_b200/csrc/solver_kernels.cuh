@@ -20,9 +20,9 @@
 #define DFSPH_EPS ((Real)1.0e-5)   /* TimeStepDFSPH::m_eps, TimeStepDFSPH.h:28 */
 
 struct FluidArrays {
-    Real4* pos;          // (x, y, z, kappa of the running solve)
-    Real4* vel;          // (vx, vy, vz, -)
-    Real4* acc;          // pressure acceleration (ax, ay, az, -)
+    Real4* pos;          // (x, y, z, kappa of the running solve); element [n] is the far-away sentinel particle
+    Real4* vel;          // (vx, vy, vz, -); [n] = 0
+    Real4* acc;          // pressure acceleration (ax, ay, az, -); [n] = 0
     Real4* bgrad;        // G_i = sum_b V_b gradW(x_i - x_b)
     Real* density;
     Real* factor;
@@ -32,9 +32,11 @@ struct FluidArrays {
     unsigned* state;
     unsigned* nnbr;      // fluid + boundary neighbour count (particle-deficiency test)
     const unsigned* tab_f;
-    const unsigned* cnt_f;
-    const unsigned* tab_b;
+    const unsigned* cnt_f;    // per particle
+    const unsigned* tcnt_f;   // per warp tile: max count of the tile rounded up to DFSPH_PAD; slots beyond a particle's
+    const unsigned* tab_b;    //   own count hold the sentinel index, so sweeps run warp-uniform, branch-free loops
     const unsigned* cnt_b;
+    const unsigned* tcnt_b;
     unsigned Kf, Kb;
     unsigned n;
 };
@@ -42,6 +44,28 @@ struct FluidArrays {
 __device__ __forceinline__ const unsigned* tab_ptr(const unsigned* tab, unsigned K, unsigned i)
 {
     return tab + (size_t)(i >> 5) * K * DFSPH_TILE + (i & 31u);
+}
+
+// Warp-uniform neighbour sweep: U gathers in flight per thread, table indices of the next batch prefetched while the
+// current batch is processed.  F provides  Data load(unsigned j)  and  void apply(const Data&).
+template <int U, class F>
+__device__ __forceinline__ void neighbor_sweep(const unsigned* __restrict__ t, unsigned count, F& f)
+{
+    if (count == 0) return;
+    unsigned jn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) jn[u] = __ldg(t + (size_t)u * DFSPH_TILE);
+    for (unsigned k = 0; k < count; k += U) {
+        typename F::Data d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) d[u] = f.load(jn[u]);
+        if (k + U < count) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) jn[u] = __ldg(t + (size_t)(k + U + u) * DFSPH_TILE);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) f.apply(d[u]);
+    }
 }
 
 // ---- block reduction helpers -----------------------------------------------------------------------------------
@@ -78,6 +102,70 @@ __device__ __forceinline__ bool last_block(Ctrl* ctrl)
 }
 
 // ---- K1+K2+K3 ------------------------------------------------------------------------------------------------------
+#ifndef DFSPH_U2
+#define DFSPH_U2 4   /* gathers in flight per thread, two-array sweeps */
+#endif
+#ifndef DFSPH_U1
+#define DFSPH_U1 4   /* one-array sweeps */
+#endif
+
+template <int MODE>
+struct InitFluidF {
+    struct Data { Real4 x, v; };
+    const Real4* pos; const Real4* vel; const SphConst& c;
+    Real4 xi, vi;
+    Real dens, gx, gy, gz, sum_grad2, dadv;
+    __device__ __forceinline__ InitFluidF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_)
+        : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), dens(0), gx(0), gy(0), gz(0), sum_grad2(0), dadv(0) {}
+    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.v = ld_gather(vel + j); return d; }
+    __device__ __forceinline__ void apply(const Data& d)
+    {
+        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        Real W, g;
+        sph_W_gradW<MODE>(c, r2, W, g);
+        const Real V = c.V;
+        dens += V * W;
+#if DFSPH_REAL_IS_DOUBLE
+        // scalar variant: grad_p_j = -V gradW; sum += |grad_p_j|^2; grad_p_i -= grad_p_j; dadv sums without V
+        const Real px = V * (g * rx), py = V * (g * ry), pz = V * (g * rz);
+        sum_grad2 += px * px + py * py + pz * pz;
+        gx += px; gy += py; gz += pz;
+        dadv += (vi.x - d.v.x) * (g * rx) + (vi.y - d.v.y) * (g * ry) + (vi.z - d.v.z) * (g * rz);
+#else
+        // AVX variant: V_gradW = gradW * V_j
+        const Real gv = g * V;
+        const Real px = rx * gv, py = ry * gv, pz = rz * gv;
+        sum_grad2 += px * px + py * py + pz * pz;
+        gx += px; gy += py; gz += pz;
+        dadv += (vi.x - d.v.x) * px + (vi.y - d.v.y) * py + (vi.z - d.v.z) * pz;
+#endif
+    }
+};
+
+template <int MODE>
+struct InitBoundaryF {
+    struct Data { Real4 x; };
+    const Real4* bpos; const SphConst& c;
+    Real4 xi, vi;
+    Real dens, bx, by, bz, dadv;
+    __device__ __forceinline__ InitBoundaryF(const Real4* bpos_, const SphConst& c_, Real4 xi_, Real4 vi_)
+        : bpos(bpos_), c(c_), xi(xi_), vi(vi_), dens(0), bx(0), by(0), bz(0), dadv(0) {}
+    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(bpos + j); return d; }
+    __device__ __forceinline__ void apply(const Data& d)   // d.x.w = V_b (0 for the sentinel)
+    {
+        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        Real W, g;
+        sph_W_gradW<MODE>(c, r2, W, g);
+        dens += d.x.w * W;
+        const Real gv = d.x.w * g;
+        const Real px = gv * rx, py = gv * ry, pz = gv * rz;
+        bx += px; by += py; bz += pz;
+        dadv += vi.x * px + vi.y * py + vi.z * pz;   // static boundary: v_b = 0
+    }
+};
+
 template <int MODE, bool DIV_SOLVER>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphConst c, const Real4* __restrict__ bpos, Ctrl* ctrl)
 {
@@ -87,69 +175,29 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphCo
     const Real4 vi = ld_gather(f.vel + i);
     const Real V = c.V;
 
-    Real dens = (Real)0.0;
-    Real gx = (Real)0.0, gy = (Real)0.0, gz = (Real)0.0;   // sum_j V gradW_ij (fluid)
-    Real sum_grad2 = (Real)0.0;
-    Real dadv = (Real)0.0;
-
-    const unsigned nf = f.cnt_f[i];
-    const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
-#pragma unroll 2
-    for (unsigned k = 0; k < nf; ++k) {
-        const unsigned j = tf[(size_t)k * DFSPH_TILE];
-        const Real4 xj = ld_plain(f.pos + j);
-        const Real4 vj = ld_gather(f.vel + j);
-        const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        Real W, g;
-        sph_W_gradW<MODE>(c, r2, W, g);
-        dens += V * W;
-#if DFSPH_REAL_IS_DOUBLE
-        // scalar variant: grad_p_j = -V gradW; sum += |grad_p_j|^2; grad_p_i -= grad_p_j; dadv sums without V
-        const Real px = V * (g * rx), py = V * (g * ry), pz = V * (g * rz);
-        sum_grad2 += px * px + py * py + pz * pz;
-        gx += px; gy += py; gz += pz;
-        dadv += (vi.x - vj.x) * (g * rx) + (vi.y - vj.y) * (g * ry) + (vi.z - vj.z) * (g * rz);
-#else
-        // AVX variant: V_gradW = gradW * V_j
-        const Real px = (rx * g) * V, py = (ry * g) * V, pz = (rz * g) * V;
-        sum_grad2 += px * px + py * py + pz * pz;
-        gx += px; gy += py; gz += pz;
-        dadv += (vi.x - vj.x) * px + (vi.y - vj.y) * py + (vi.z - vj.z) * pz;
-#endif
-    }
+    InitFluidF<MODE> ff(f, c, xi, vi);
+    neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], ff);
+    Real dadv = ff.dadv;
 #if DFSPH_REAL_IS_DOUBLE
     dadv *= V;   // "assumes that all fluid particles have the same volume" (TimeStepDFSPH.cpp:1266-1267)
 #endif
 
     // Akinci2012 boundary neighbours (static bodies: v_b = 0)
-    Real bx = (Real)0.0, by = (Real)0.0, bz = (Real)0.0;
-    const unsigned nb = f.cnt_b[i];
-    const unsigned* tb = tab_ptr(f.tab_b, f.Kb, i);
-    for (unsigned k = 0; k < nb; ++k) {
-        const unsigned j = tb[(size_t)k * DFSPH_TILE];
-        const Real4 xb = ld_gather(bpos + j);   // w = V_b
-        const Real rx = xi.x - xb.x, ry = xi.y - xb.y, rz = xi.z - xb.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        Real W, g;
-        sph_W_gradW<MODE>(c, r2, W, g);
-        dens += xb.w * W;
-        const Real px = xb.w * (g * rx), py = xb.w * (g * ry), pz = xb.w * (g * rz);
-        bx += px; by += py; bz += pz;
-        dadv += vi.x * px + vi.y * py + vi.z * pz;
-    }
+    InitBoundaryF<MODE> fb(bpos, c, xi, vi);
+    neighbor_sweep<DFSPH_U1>(tab_ptr(f.tab_b, f.Kb, i), f.tcnt_b[i >> 5], fb);
+    dadv += fb.dadv;
 
     // density (TimeStep.cpp:70,110 / 133,166)
-    const Real density = (V * c.W_zero + dens) * c.density0;
+    const Real density = (V * c.W_zero + (ff.dens + fb.dens)) * c.density0;
     f.density[i] = density;
-    st_real4(f.bgrad + i, make_real4(bx, by, bz, (Real)0.0));
+    st_real4(f.bgrad + i, make_real4(fb.bx, fb.by, fb.bz, (Real)0.0));
 
     // factor (TimeStepDFSPH.cpp:812-821 / 1170-1182)
-    gx += bx; gy += by; gz += bz;
-    sum_grad2 += gx * gx + gy * gy + gz * gz;
+    const Real gx = ff.gx + fb.bx, gy = ff.gy + fb.by, gz = ff.gz + fb.bz;
+    const Real sum_grad2 = ff.sum_grad2 + (gx * gx + gy * gy + gz * gz);
     Real factor = sum_grad2 > DFSPH_EPS ? (Real)1.0 / sum_grad2 : (Real)0.0;
 
-    const unsigned nn = nf + nb;
+    const unsigned nn = f.cnt_f[i] + f.cnt_b[i];
     f.nnbr[i] = nn;
 
     if (DIV_SOLVER) {
@@ -169,53 +217,83 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphCo
 
 // ---- pressure acceleration of particle i from the kappa values in pos.w -------------------------------------------
 template <int MODE>
-__device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphConst& c, unsigned i, const Real4 xi, Real& ax, Real& ay, Real& az)
-{
-    const Real ki = xi.w;
-    const Real V = c.V;
-    ax = ay = az = (Real)0.0;
-    const unsigned nf = f.cnt_f[i];
-    const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
-#pragma unroll 4
-    for (unsigned k = 0; k < nf; ++k) {
-        const unsigned j = tf[(size_t)k * DFSPH_TILE];
-        const Real4 xj = ld_plain(f.pos + j);
-        const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+struct AccelF {
+    struct Data { Real4 x; };
+    const Real4* pos; const SphConst& c;
+    Real4 xi;
+    Real ax, ay, az;
+    __device__ __forceinline__ AccelF(const FluidArrays& f, const SphConst& c_, Real4 xi_) : pos(f.pos), c(c_), xi(xi_), ax(0), ay(0), az(0) {}
+    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(pos + j); return d; }
+    __device__ __forceinline__ void apply(const Data& d)
+    {
+        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
         const Real r2 = rx * rx + ry * ry + rz * rz;
         const Real g = sph_gradW_scale<MODE>(c, r2);
-        const Real pSum = ki + xj.w;   // density0 ratio is 1 (single phase)
+        const Real pSum = xi.w + d.x.w;   // density0 ratio is 1 (single phase)
 #if DFSPH_REAL_IS_DOUBLE
         if (real_abs(pSum) > DFSPH_EPS) {   // scalar variant skips tiny sums (TimeStepDFSPH.cpp:1323-1327)
-            const Real s = -V * g * pSum;
+            const Real s = -c.V * g * pSum;
             ax += s * rx; ay += s * ry; az += s * rz;
         }
 #else
-        const Real s = (g * V) * pSum;      // delta_ai -= V_gradW * pSum (TimeStepDFSPH.cpp:987)
+        const Real s = (g * c.V) * pSum;    // delta_ai -= V_gradW * pSum (TimeStepDFSPH.cpp:987)
         ax -= s * rx; ay -= s * ry; az -= s * rz;
 #endif
     }
+};
+
+template <int MODE>
+__device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphConst& c, unsigned i, const Real4 xi, Real& ax, Real& ay, Real& az)
+{
+    AccelF<MODE> fa(f, c, xi);
+    neighbor_sweep<DFSPH_U1>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fa);
+    ax = fa.ax; ay = fa.ay; az = fa.az;
+    const Real ki = xi.w;
     if (real_abs(ki) > DFSPH_EPS) {          // boundary term (:993-1010 / 1333-1345): a_i -= kappa_i * G_i
         const Real4 b = ld_gather(f.bgrad + i);
         ax -= ki * b.x; ay -= ki * b.y; az -= ki * b.z;
     }
 }
 
+// Non-active particles (emitter-animated / fixed) keep a zero pressure acceleration; their lanes still walk the
+// warp-uniform loop (results discarded) so that the sweep stays convergent.
 template <int MODE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_accel(FluidArrays f, SphConst c, const Ctrl* __restrict__ ctrl)
 {
     if (ctrl->done) return;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= f.n) return;
-    Real ax = (Real)0.0, ay = (Real)0.0, az = (Real)0.0;
-    if (f.state[i] == 0u) {
-        const Real4 xi = ld_plain(f.pos + i);
-        pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
-    }
+    Real ax, ay, az;
+    const Real4 xi = ld_gather(f.pos + i);
+    pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+    if (f.state[i] != 0u) { ax = ay = az = (Real)0.0; }
     st_real4(f.acc + i, make_real4(ax, ay, az, (Real)0.0));
 }
 
 // ---- pass B --------------------------------------------------------------------------------------------------------
 enum { SOLVE_DIV = 0, SOLVE_PRESS = 1 };
+
+template <int MODE>
+struct JacobiF {
+    struct Data { Real4 x, a; };
+    const Real4* pos; const Real4* acc; const SphConst& c;
+    Real4 xi, ai;
+    Real sum;
+    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), xi(xi_), ai(ai_), sum(0) {}
+    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.a = ld_gather(acc + j); return d; }
+    __device__ __forceinline__ void apply(const Data& d)
+    {
+        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        const Real g = sph_gradW_scale<MODE>(c, r2);
+#if DFSPH_REAL_IS_DOUBLE
+        sum += (ai.x - d.a.x) * (g * rx) + (ai.y - d.a.y) * (g * ry) + (ai.z - d.a.z) * (g * rz);
+#else
+        const Real s = g * c.V;
+        sum += (ai.x - d.a.x) * (rx * s) + (ai.y - d.a.y) * (ry * s) + (ai.z - d.a.z) * (rz * s);
+#endif
+    }
+};
 
 template <int MODE, int SOLVE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial)
@@ -223,44 +301,30 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst 
     if (ctrl->done) return;
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     double err = 0.0;
-    if (i < f.n && (SOLVE == SOLVE_DIV || f.state[i] == 0u)) {
+    if (i < f.n) {
         const Real h = ctrl->h;
         const Real4 xi = ld_plain(f.pos + i);
         const Real4 ai = ld_gather(f.acc + i);
-        const Real V = c.V;
-        Real sum = (Real)0.0;
-        const unsigned nf = f.cnt_f[i];
-        const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
-#pragma unroll 4
-        for (unsigned k = 0; k < nf; ++k) {
-            const unsigned j = tf[(size_t)k * DFSPH_TILE];
-            const Real4 xj = ld_plain(f.pos + j);
-            const Real4 aj = ld_gather(f.acc + j);
-            const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
-            const Real r2 = rx * rx + ry * ry + rz * rz;
-            const Real g = sph_gradW_scale<MODE>(c, r2);
+        JacobiF<MODE> fj(f, c, xi, ai);
+        neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fj);
+        Real sum = fj.sum;
 #if DFSPH_REAL_IS_DOUBLE
-            sum += (ai.x - aj.x) * (g * rx) + (ai.y - aj.y) * (g * ry) + (ai.z - aj.z) * (g * rz);
-#else
-            const Real s = g * V;
-            sum += (ai.x - aj.x) * (rx * s) + (ai.y - aj.y) * (ry * s) + (ai.z - aj.z) * (rz * s);
-#endif
-        }
-#if DFSPH_REAL_IS_DOUBLE
-        sum *= V;
+        sum *= c.V;
 #endif
         const Real4 b = ld_gather(f.bgrad + i);
         sum += ai.x * b.x + ai.y * b.y + ai.z * b.z;
 
-        Real aij_pj = sum;
-        Real s_i;
-        if (SOLVE == SOLVE_PRESS) { aij_pj *= h * h; s_i = (Real)1.0 - f.density_adv[i]; }
-        else { aij_pj *= h; s_i = -f.density_adv[i]; }
-        Real residuum = real_min(s_i - aij_pj, (Real)0.0);
-        if (SOLVE == SOLVE_DIV && f.nnbr[i] < 20u) residuum = (Real)0.0;
-        const Real knew = real_max(xi.w - (Real)0.5 * (s_i - aij_pj) * f.factor[i], (Real)0.0);
-        f.pos[i].w = knew;
-        err = -(double)(c.density0 * residuum);
+        if (SOLVE == SOLVE_DIV || f.state[i] == 0u) {
+            Real aij_pj = sum;
+            Real s_i;
+            if (SOLVE == SOLVE_PRESS) { aij_pj *= h * h; s_i = (Real)1.0 - f.density_adv[i]; }
+            else { aij_pj *= h; s_i = -f.density_adv[i]; }
+            Real residuum = real_min(s_i - aij_pj, (Real)0.0);
+            if (SOLVE == SOLVE_DIV && f.nnbr[i] < 20u) residuum = (Real)0.0;
+            const Real knew = real_max(xi.w - (Real)0.5 * (s_i - aij_pj) * f.factor[i], (Real)0.0);
+            f.pos[i].w = knew;
+            err = -(double)(c.density0 * residuum);
+        }
     }
     // density-error reduction: block partials, summed in fixed order by the last block (deterministic)
     const double bsum = block_sum_double(err);
@@ -309,9 +373,10 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_div_final(FluidArrays f, SphCon
         Real4 v = ld_gather(f.vel + i);
         const unsigned st = f.state[i];
         if (DIV_SOLVER) {
-            const Real4 xi = ld_plain(f.pos + i);
-            Real ax = (Real)0.0, ay = (Real)0.0, az = (Real)0.0;
-            if (st == 0u) pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+            const Real4 xi = ld_gather(f.pos + i);
+            Real ax, ay, az;
+            pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+            if (st != 0u) { ax = ay = az = (Real)0.0; }
             st_real4(f.acc + i, make_real4(ax, ay, az, (Real)0.0));
             v.x += h * ax; v.y += h * ay; v.z += h * az;                 // TimeStepDFSPH.cpp:516
             f.factor[i] *= h;                                            // :518
@@ -374,6 +439,28 @@ __global__ void k_update_time_step(Ctrl* ctrl, SolverParams sp)
 
 // ---- pressure solve init -------------------------------------------------------------------------------------------
 template <int MODE>
+struct VelDivF {
+    struct Data { Real4 x, v; };
+    const Real4* pos; const Real4* vel; const SphConst& c;
+    Real4 xi, vi;
+    Real delta;
+    __device__ __forceinline__ VelDivF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_) : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), delta(0) {}
+    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.v = ld_gather(vel + j); return d; }
+    __device__ __forceinline__ void apply(const Data& d)
+    {
+        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
+        const Real r2 = rx * rx + ry * ry + rz * rz;
+        const Real g = sph_gradW_scale<MODE>(c, r2);
+#if DFSPH_REAL_IS_DOUBLE
+        delta += (vi.x - d.v.x) * (g * rx) + (vi.y - d.v.y) * (g * ry) + (vi.z - d.v.z) * (g * rz);
+#else
+        const Real s = g * c.V;
+        delta += (vi.x - d.v.x) * (rx * s) + (vi.y - d.v.y) * (ry * s) + (vi.z - d.v.z) * (rz * s);
+#endif
+    }
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_init(FluidArrays f, SphConst c, Ctrl* ctrl)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,27 +468,11 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_init(FluidArrays f, SphCo
     const Real h = ctrl->h;     // the NEW time step size (TimeStepDFSPH.cpp:254)
     const Real4 xi = ld_plain(f.pos + i);
     const Real4 vi = ld_gather(f.vel + i);
-    const Real V = c.V;
-    Real delta = (Real)0.0;
-    const unsigned nf = f.cnt_f[i];
-    const unsigned* tf = tab_ptr(f.tab_f, f.Kf, i);
-#pragma unroll 4
-    for (unsigned k = 0; k < nf; ++k) {
-        const unsigned j = tf[(size_t)k * DFSPH_TILE];
-        const Real4 xj = ld_plain(f.pos + j);
-        const Real4 vj = ld_gather(f.vel + j);
-        const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        const Real g = sph_gradW_scale<MODE>(c, r2);
+    VelDivF<MODE> fv(f, c, xi, vi);
+    neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fv);
+    Real delta = fv.delta;
 #if DFSPH_REAL_IS_DOUBLE
-        delta += (vi.x - vj.x) * (g * rx) + (vi.y - vj.y) * (g * ry) + (vi.z - vj.z) * (g * rz);
-#else
-        const Real s = g * V;
-        delta += (vi.x - vj.x) * (rx * s) + (vi.y - vj.y) * (ry * s) + (vi.z - vj.z) * (rz * s);
-#endif
-    }
-#if DFSPH_REAL_IS_DOUBLE
-    delta *= V;
+    delta *= c.V;
 #endif
     const Real4 b = ld_gather(f.bgrad + i);
     delta += vi.x * b.x + vi.y * b.y + vi.z * b.z;
@@ -424,10 +495,11 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_final(FluidArrays f, SphC
     if (i >= f.n) return;
     const Real h = ctrl->h;
     const Real hs = ctrl->h_step;
-    const Real4 xi = ld_plain(f.pos + i);
+    const Real4 xi = ld_gather(f.pos + i);
     const unsigned st = f.state[i];
-    Real ax = (Real)0.0, ay = (Real)0.0, az = (Real)0.0;
-    if (st == 0u) pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+    Real ax, ay, az;
+    pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+    if (st != 0u) { ax = ay = az = (Real)0.0; }
     st_real4(f.acc + i, make_real4(ax, ay, az, (Real)0.0));
     Real4 v = ld_gather(f.vel + i);
     v.x += h * ax; v.y += h * ay; v.z += h * az;                  // :360

