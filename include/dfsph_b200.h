@@ -171,6 +171,28 @@ uint64_t dfsph_b200_num_boundary_particles(const dfsph_b200_ctx* ctx);
  * Lets the reference's Tests/Kernel/KernelTests.cpp checks run against the device implementations. */
 int dfsph_b200_eval_kernel(dfsph_b200_ctx* ctx, int kernel, uint64_t n, const void* r, void* W, void* gradW);
 
+/* Device timing.  timer_start/stop bracket any number of calls with two CUDA events on the context's own stream
+ * (the stream every kernel of this library is launched on).  With profiling on, every launch of the kernel classes
+ * below is additionally bracketed by its own event pair; get_profile returns accumulated milliseconds and launch
+ * counts per class since profiling was switched on.  (Mirrors the reference's START_TIMING/STOP_TIMING_AVG timers
+ * "neighborhood_search", "divergenceSolve", "pressureSolve": Simulation.cpp:616, TimeStepDFSPH.cpp:166,213.) */
+enum {
+    DFSPH_B200_PROF_SORT = 0,         /* cell counting sort + reorder */
+    DFSPH_B200_PROF_BUILD = 1,        /* neighbour table */
+    DFSPH_B200_PROF_INIT = 2,         /* K1+K2+K3 density / factor / divergence source */
+    DFSPH_B200_PROF_ACCEL = 3,        /* pass A of an iteration */
+    DFSPH_B200_PROF_JACOBI_DIV = 4,   /* pass B, divergence solve */
+    DFSPH_B200_PROF_JACOBI_PRESS = 5, /* pass B, pressure solve */
+    DFSPH_B200_PROF_DIV_FINAL = 6,
+    DFSPH_B200_PROF_PRESS_INIT = 7,
+    DFSPH_B200_PROF_PRESS_FINAL = 8,
+    DFSPH_B200_PROF_CLASSES = 9
+};
+int dfsph_b200_set_profiling(dfsph_b200_ctx* ctx, int on);
+int dfsph_b200_get_profile(dfsph_b200_ctx* ctx, double* ms /*[DFSPH_B200_PROF_CLASSES]*/, uint64_t* count);
+int dfsph_b200_timer_start(dfsph_b200_ctx* ctx);
+int dfsph_b200_timer_stop(dfsph_b200_ctx* ctx, float* ms);
+
 /* Pinned host buffers for the host-buffer path (dfsph_b200_step_host) and an explicit stream synchronise. */
 void* dfsph_b200_alloc_pinned(size_t bytes);
 void dfsph_b200_free_pinned(void* p);

@@ -669,6 +669,21 @@ int ref_set_state(int, const Real* x, const Real* v)
     return 0;
 }
 
+int ref_set_field(int, const char* name, const Real* in, int dim)
+{
+    const std::string s(name);
+    const size_t n = g->x.size();
+    std::vector<V3>* v3 = nullptr;
+    std::vector<Real>* v1 = nullptr;
+    if (s == "position") v3 = &g->x; else if (s == "velocity") v3 = &g->v;
+    else if (s == "p / rho^2") v1 = &g->kappa; else if (s == "p_v / rho^2") v1 = &g->kappa_v;
+    else return -1;
+    if (v3) for (size_t i = 0; i < n; ++i) (*v3)[i] = { in[3 * i], in[3 * i + 1], in[3 * i + 2] };
+    if (v1) for (size_t i = 0; i < n; ++i) (*v1)[i] = in[i];
+    (void)dim;
+    return 0;
+}
+
 int ref_get_boundary(int, Real* x, Real* V)
 {
     for (size_t i = 0; i < g->bx.size(); ++i) {

@@ -242,6 +242,20 @@ int ref_set_state(int fluid, const Real* x, const Real* v)
 	return 0;
 }
 
+/* Overwrite a scalar/vector particle field (array order) through the reference's own FieldDescription accessor. */
+int ref_set_field(int fluid, const char* name, const Real* in, int dim)
+{
+	FluidModel* fm = Simulation::getCurrent()->getFluidModel(fluid);
+	const unsigned int n = fm->numActiveParticles();
+	const FieldDescription& f = fm->getField(name);
+	for (unsigned int i = 0; i < n; i++)
+	{
+		Real* p = (Real*)f.getFct(i);
+		for (int k = 0; k < dim; k++) p[k] = in[dim * i + k];
+	}
+	return 0;
+}
+
 int ref_get_boundary(int b, Real* x, Real* V)
 {
 	BoundaryModel_Akinci2012* bm = static_cast<BoundaryModel_Akinci2012*>(Simulation::getCurrent()->getBoundaryModel(b));

@@ -56,6 +56,7 @@ class RefSim:
         L.ref_num_boundary_particles.argtypes = [C.c_int]
         L.ref_get_field.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_int]
         L.ref_get_ids.argtypes = [C.c_int, C.c_void_p]
+        L.ref_set_field.argtypes = [C.c_int, C.c_char_p, C.c_void_p, C.c_int]
         L.ref_set_state.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.ref_get_boundary.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.ref_neighbor_counts.argtypes = [C.c_int, C.c_int, C.c_void_p]
@@ -160,6 +161,12 @@ class RefSim:
         out = np.empty_like(f)
         out[self.ids(fluid)] = f
         return out
+
+    def set_field_by_id(self, name, arr, fluid=0):
+        """Overwrite position / velocity / p / rho^2 / p_v / rho^2; row k of ``arr`` belongs to the particle with id k."""
+        arr = np.ascontiguousarray(np.asarray(arr, dtype=self.dtype)[self.ids(fluid)])
+        if self.lib.ref_set_field(fluid, name.encode(), arr.ctypes.data, FIELDS[name]) != 0:
+            raise KeyError(name)
 
     def set_state(self, x=None, v=None, fluid=0):
         xp = vp = None

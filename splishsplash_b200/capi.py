@@ -60,7 +60,11 @@ EXPORTS = [
     "dfsph_b200_step", "dfsph_b200_step_host", "dfsph_b200_download", "dfsph_b200_upload", "dfsph_b200_neighbors",
     "dfsph_b200_search_and_density", "dfsph_b200_num_particles", "dfsph_b200_num_boundary_particles",
     "dfsph_b200_eval_kernel", "dfsph_b200_alloc_pinned", "dfsph_b200_free_pinned", "dfsph_b200_synchronize",
+    "dfsph_b200_set_profiling", "dfsph_b200_get_profile", "dfsph_b200_timer_start", "dfsph_b200_timer_stop",
 ]
+
+PROF_CLASSES = ["sort", "build_neighbors", "init_sweep", "accel", "jacobi_div", "jacobi_press", "div_final",
+                "press_init", "press_final"]
 
 
 def lib_path(precision: str) -> str:
@@ -108,6 +112,10 @@ def load(precision: str = "f32"):
     L.dfsph_b200_alloc_pinned.restype = P
     L.dfsph_b200_free_pinned.argtypes = [P]
     L.dfsph_b200_synchronize.argtypes = [P]
+    L.dfsph_b200_set_profiling.argtypes = [P, C.c_int]
+    L.dfsph_b200_get_profile.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.dfsph_b200_timer_start.argtypes = [P]
+    L.dfsph_b200_timer_stop.argtypes = [P, C.POINTER(C.c_float)]
     want = 4 if precision == "f32" else 8
     if L.dfsph_b200_sizeof_real() != want:
         raise RuntimeError(f"{path}: sizeof(Real) mismatch")

@@ -74,7 +74,43 @@ struct dfsph_b200_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     void* stage = nullptr;       // device staging for AoS transfers
     size_t stage_bytes = 0;
+
+    // optional per-kernel-class device timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct ProfRec { int cls; int seq; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[DFSPH_B200_PROF_CLASSES] = {0};
+    uint64_t prof_count[DFSPH_B200_PROF_CLASSES] = {0};
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
 };
+
+struct ProfScope {
+    dfsph_b200_ctx* c; cudaEvent_t b = nullptr;
+    ProfScope(dfsph_b200_ctx* c_, int cls, int seq = -1) : c(c_)
+    {
+        if (!c->profiling) return;
+        cudaEvent_t e[2];
+        for (int k = 0; k < 2; ++k) {
+            if (!c->prof_pool.empty()) { e[k] = c->prof_pool.back(); c->prof_pool.pop_back(); }
+            else cudaEventCreate(&e[k]);
+        }
+        cudaEventRecord(e[0], c->stream);
+        b = e[1];
+        c->prof_recs.push_back({cls, seq, e[0], e[1]});
+    }
+    ~ProfScope() { if (b) cudaEventRecord(b, c->stream); }
+};
+
+static void prof_collect(dfsph_b200_ctx* c)   // call after a stream synchronise
+{
+    for (auto& r : c->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.cls] += ms; c->prof_count[r.cls]++; }
+        c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
+}
 
 #define CTX_FAIL(ctx, code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); (ctx)->err = _b; return (code); } while (0)
 #define CUDA_TRY(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { (ctx)->sticky = 1; \
@@ -282,6 +318,10 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     for (int k = 0; k < 3; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+    for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->prof_pool) cudaEventDestroy(e);
+    if (c->timer_a) cudaEventDestroy(c->timer_a);
+    if (c->timer_b) cudaEventDestroy(c->timer_b);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return DFSPH_B200_OK;
@@ -658,14 +698,17 @@ static int run_search(dfsph_b200_ctx* c)
 {
     const unsigned n = c->n;
     cudaStream_t st = c->stream;
-    int rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start);
+    int rc;
+    { ProfScope ps(c, DFSPH_B200_PROF_SORT); rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start); }
     if (rc) return rc;
     if (n > 0) {
         const int src = c->cur, dst = 1 - c->cur;
         const int psrc = c->cur_pos, pdst = 1 - c->cur_pos;
+        { ProfScope ps(c, DFSPH_B200_PROF_SORT);
         k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
-            c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc);
+            c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc); }
         c->cur = dst; c->cur_pos = pdst;
+        ProfScope ps(c, DFSPH_B200_PROF_BUILD);
         k_build_neighbors<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
             c->bpos, c->bcell_start, c->nb, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl);
         c->launches += 2;
@@ -685,8 +728,9 @@ static int run_solver(dfsph_b200_ctx* c)
     const bool div = c->par.enable_divergence_solver != 0;
     FluidArrays f = fluid_arrays(c);
 
+    { ProfScope ps(c, DFSPH_B200_PROF_INIT);
     if (div) k_init_sweep<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl);
-    else k_init_sweep<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl);
+    else k_init_sweep<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl); }
     c->launches++;
 
     auto solve_loop = [&](int solve, unsigned max_it, unsigned& pred) -> int {
@@ -694,11 +738,13 @@ static int run_solver(dfsph_b200_ctx* c)
         c->launches++;
         unsigned launched = 0;
         unsigned batch = std::min(std::max(pred + 1u, 2u), max_it);
+        const size_t prof_start = c->prof_recs.size();
         while (true) {
             for (unsigned b = 0; b < batch; ++b) {
-                k_accel<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl);
-                if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial);
-                else k_jacobi<MODE, SOLVE_PRESS><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial);
+                const int seq = (int)(launched + b);
+                { ProfScope ps(c, DFSPH_B200_PROF_ACCEL, seq); k_accel<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl); }
+                if (solve == SOLVE_DIV) { ProfScope ps(c, DFSPH_B200_PROF_JACOBI_DIV, seq); k_jacobi<MODE, SOLVE_DIV><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial); }
+                else { ProfScope ps(c, DFSPH_B200_PROF_JACOBI_PRESS, seq); k_jacobi<MODE, SOLVE_PRESS><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial); }
                 c->launches += 2;
             }
             launched += batch;
@@ -708,6 +754,13 @@ static int run_solver(dfsph_b200_ctx* c)
             batch = std::min(2u, max_it - launched);
         }
         pred = c->h_ctrl->iter;
+        // launches past the converged iteration exited immediately: keep them out of the per-kernel statistics
+        for (size_t r = prof_start; r < c->prof_recs.size();) {
+            if (c->prof_recs[r].seq >= (int)pred) {
+                c->prof_pool.push_back(c->prof_recs[r].a); c->prof_pool.push_back(c->prof_recs[r].b);
+                c->prof_recs.erase(c->prof_recs.begin() + r);
+            } else ++r;
+        }
         return 0;
     };
 
@@ -715,19 +768,21 @@ static int run_solver(dfsph_b200_ctx* c)
         // the reference's iteration is a no-op for an empty model: avg stays 0, one iteration is counted
         int rc = solve_loop(SOLVE_DIV, c->par.max_iterations_v, c->pred_iter_v);
         if (rc) return rc;
+        ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
         k_div_final<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
     } else {
+        ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
         k_div_final<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
     }
     k_update_time_step<<<1, 1, 0, st>>>(c->ctrl, sp);
-    k_press_init<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl);
+    { ProfScope ps(c, DFSPH_B200_PROF_PRESS_INIT); k_press_init<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl); }
     c->launches += 3;
     {
         int rc = solve_loop(SOLVE_PRESS, c->par.max_iterations, c->pred_iter);
         if (rc) return rc;
     }
     Real4* pos_out = c->pos[1 - c->cur_pos];
-    k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out);
+    { ProfScope ps(c, DFSPH_B200_PROF_PRESS_FINAL); k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out); }
     k_step_end<<<1, 1, 0, st>>>(c->ctrl);
     c->launches += 2;
     c->cur_pos = 1 - c->cur_pos;
@@ -760,6 +815,7 @@ static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
     if (stats) {
         CUDA_TRY(c, cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
+        prof_collect(c);
         const Ctrl& hc = *c->h_ctrl;
         memset(stats, 0, sizeof(*stats));
         stats->iterations = hc.iterations;
@@ -1042,7 +1098,45 @@ void* dfsph_b200_alloc_pinned(size_t bytes)
 }
 void dfsph_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
-// device time of the whole stream so far: callers time with their own events through these
+int dfsph_b200_set_profiling(dfsph_b200_ctx* c, int on)
+{
+    CHECK_CTX(c);
+    c->profiling = on != 0;
+    if (on) { for (int k = 0; k < DFSPH_B200_PROF_CLASSES; ++k) { c->prof_ms[k] = 0.0; c->prof_count[k] = 0; } }
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_get_profile(dfsph_b200_ctx* c, double* ms, uint64_t* count)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    for (int k = 0; k < DFSPH_B200_PROF_CLASSES; ++k) { if (ms) ms[k] = c->prof_ms[k]; if (count) count[k] = c->prof_count[k]; }
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_timer_start(dfsph_b200_ctx* c)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!c->timer_a) { CUDA_TRY(c, cudaEventCreate(&c->timer_a)); CUDA_TRY(c, cudaEventCreate(&c->timer_b)); }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->timer_a, c->stream));
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_timer_stop(dfsph_b200_ctx* c, float* ms)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!c->timer_a || !ms) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "timer_start has not been called");
+    CUDA_TRY(c, cudaEventRecord(c->timer_b, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(c->timer_b));
+    CUDA_TRY(c, cudaEventElapsedTime(ms, c->timer_a, c->timer_b));
+    return DFSPH_B200_OK;
+}
+
 int dfsph_b200_synchronize(dfsph_b200_ctx* c)
 {
     CHECK_CTX(c);

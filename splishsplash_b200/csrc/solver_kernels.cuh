@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst 
         if (threadIdx.x == 0) {
             // loop control (TimeStepDFSPH.cpp:324-341 / 477-495)
             const Real density_error = (Real)t;
-            const Real avg = density_error / (Real)f.n;
+            const Real avg = f.n > 0u ? density_error / (Real)f.n : (Real)0.0;   // empty model: iteration is a no-op (:550-551)
             Real eta;
             unsigned min_it, max_it;
             if (SOLVE == SOLVE_PRESS) { eta = sp.max_error * (Real)0.01 * c.density0; min_it = sp.min_iter; max_it = sp.max_iter; }

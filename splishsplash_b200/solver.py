@@ -189,6 +189,25 @@ class TimeStepDFSPH_B200:
         self._pinned.append(p)
         return arr
 
+    def set_profiling(self, on=True):
+        self._check(self.lib.dfsph_b200_set_profiling(self.ctx, 1 if on else 0))
+
+    def profile(self):
+        """{kernel class: (total ms, launches)} accumulated since set_profiling(True)."""
+        n = len(capi.PROF_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_uint64 * n)()
+        self._check(self.lib.dfsph_b200_get_profile(self.ctx, ms, cnt))
+        return {capi.PROF_CLASSES[k]: (float(ms[k]), int(cnt[k])) for k in range(n)}
+
+    def timer_start(self):
+        self._check(self.lib.dfsph_b200_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self.lib.dfsph_b200_timer_stop(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
     def synchronize(self):
         self._check(self.lib.dfsph_b200_synchronize(self.ctx))
 

@@ -1,0 +1,73 @@
+"""Generates the golden fixtures in this directory from the REFERENCE ITSELF (oracle/_ref = the reference's unmodified
+DFSPH sources compiled by oracle/Makefile; needs /root/reference at build time, not at run time).
+
+    python tests/golden/make_golden.py
+
+Each fixture stores, for a sequence of steps, the exact input state of the step (x, v, kappa, kappa_v by particle id,
+time step size) and every per-step output field of the reference, plus the neighbour sets of the initial state and the
+boundary volumes.  Tests replay each step from the stored input on the oracle port (CPU) and on the CUDA library (GPU).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refsim  # noqa: E402
+from splishsplash_b200 import scenes  # noqa: E402
+from tests.parity import STEP_FIELDS, neighbor_sets_by_id  # noqa: E402
+
+FIXTURES = [  # name, scene factory, precision, kernel, steps, params
+    ("dambreak_tiny_f32_k4", lambda dt: scenes.dam_break("tiny", dtype=dt), "f32", 4, 8, {}),
+    ("dambreak_tiny_f64_k4", lambda dt: scenes.dam_break("tiny", dtype=dt), "f64", 4, 8, {}),
+    ("dambreak_tiny_f64_k0", lambda dt: scenes.dam_break("tiny", dtype=dt), "f64", 0, 3, {}),
+    ("rwstate_f64_k4", lambda dt: scenes.rw_state_scene(dtype=dt), "f64", 4, 2,
+     dict(timeStepSize=0.005, cflFactor=1.0, maxError=0.05)),   # data/Scenes/ReadWriteStateTest.json settings
+]
+
+
+def main():
+    for name, factory, prec, kernel, steps, params in FIXTURES:
+        dt = np.float32 if prec == "f32" else np.float64
+        sc = factory(dt)
+        sim = refsim.build_ref_scene(sc, prec, kernel=kernel, **params)
+        out = {"fluid_x": sc["fluid_x"], "boundary_x": sc["boundary_x"], "radius": np.float64(sc["radius"]),
+               "kernel": np.int32(kernel), "steps": np.int32(steps)}
+        for k, v in params.items():
+            out["param_" + k] = np.float64(v)
+        bx, bV = sim.boundary(0)
+        key = lambda a: [tuple(r) for r in a.tolist()]
+        d = dict(zip(key(bx), bV.tolist()))
+        out["boundary_V"] = np.array([d[k] for k in key(np.asarray(sc["boundary_x"], dtype=dt))], dtype=dt)
+        sim.search_and_density()
+        rid = sim.ids()
+        c, o, i = sim.neighbors(0, 0)
+        nc, nl = neighbor_sets_by_id(c, o, i, rid, rid)
+        out["nbr_f_counts"], out["nbr_f_ids"] = nc, nl
+        ins = {k: n for n, k in enumerate(key(np.asarray(sc["boundary_x"], dtype=dt)))}
+        rmap = np.array([ins[k] for k in key(bx)], dtype=np.uint32)
+        c, o, i = sim.neighbors(0, 1)
+        nc, nl = neighbor_sets_by_id(c, o, i, rid, rmap)
+        out["nbr_b_counts"], out["nbr_b_ids"] = nc, nl
+        out["density0"] = sim.field_by_id("density")
+        for s in range(steps):
+            for f in ("position", "velocity", "p / rho^2", "p_v / rho^2"):
+                out[f"in{s}_{f}"] = sim.field_by_id(f)
+            out[f"in{s}_h"] = np.float64(sim.h)
+            sim.step(1)
+            for f in STEP_FIELDS:
+                out[f"out{s}_{f}"] = sim.field_by_id(f)
+            out[f"out{s}_h"] = np.float64(sim.h)
+            out[f"out{s}_iters"] = np.array([sim.iterations_v, sim.iterations], dtype=np.int32)
+        sim.destroy()
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(name, "N =", len(sc["fluid_x"]), "Nb =", len(sc["boundary_x"]), os.path.getsize(path) // 1024, "KiB",
+              "iters", [out[f"out{s}_iters"].tolist() for s in range(steps)])
+
+
+if __name__ == "__main__":
+    main()
