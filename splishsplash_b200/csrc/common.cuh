@@ -55,9 +55,11 @@ __device__ __forceinline__ void st_real4(Real4* p, Real4 v)
 // ---------------------------------------------------------------------------------------------------------------
 // Cell grid: cell edge S >= support radius R (S = R * (1 + 1e-5): two particles that pass the predicate
 // l2 < R*R are then at most one cell apart on every axis even with rounding in the cell computation, which is
-// done in double).  Cells are ordered in "blocked z-order": 8x8x8-cell blocks in row-major order (x slowest), cells
-// inside a block by their 9-bit Morton code.  Table size stays proportional to the domain (no power-of-two blow-up)
-// while the particles of any 2^k-aligned sub-brick are contiguous in memory.
+// done in double).  Cells are ordered along a z-order (Morton) curve, two-level so that the cell table stays
+// proportional to the domain (no power-of-two blow-up): 8x8x8-cell blocks are ranked by the Morton code of their
+// block coordinates (host-built rank table), cells inside a block by their 9-bit Morton code (z most significant).
+// Inside a cell, particles are ordered by the Morton code of their 1/8-cell sub-position (search_kernels.cuh), so
+// consecutive lanes of a warp are spatial neighbours and their neighbour lists walk memory in step.
 // ---------------------------------------------------------------------------------------------------------------
 struct GridDesc {
     double ox, oy, oz;      // origin
@@ -65,6 +67,7 @@ struct GridDesc {
     int nx, ny, nz;         // cells per axis
     int nby, nbz;           // blocks per axis (y, z)
     unsigned num_keys;      // nbx * nby * nbz * 512
+    const unsigned* block_rank;   // [nbx*nby*nbz] position of each 8^3-cell block along the z-order curve over blocks
 };
 
 __host__ __device__ __forceinline__ unsigned spread3(unsigned v)   // 3 bits -> bits 0,3,6
@@ -75,7 +78,11 @@ __host__ __device__ __forceinline__ unsigned cell_key(int cx, int cy, int cz, co
 {
     const unsigned b = ((unsigned)(cx >> 3) * (unsigned)g.nby + (unsigned)(cy >> 3)) * (unsigned)g.nbz + (unsigned)(cz >> 3);
     const unsigned l = spread3((unsigned)cx & 7u) | (spread3((unsigned)cy & 7u) << 1) | (spread3((unsigned)cz & 7u) << 2);
-    return b * 512u + l;
+#ifdef __CUDA_ARCH__
+    return __ldg(g.block_rank + b) * 512u + l;
+#else
+    return b * 512u + l;   // host code never needs the curve position
+#endif
 }
 __host__ __device__ __forceinline__ int cell_coord(Real x, double o, double inv, int n)
 {
@@ -83,6 +90,18 @@ __host__ __device__ __forceinline__ int cell_coord(Real x, double o, double inv,
     int c = (int)floor(t);
     c = c < 0 ? 0 : c;
     return c >= n ? n - 1 : c;
+}
+// cell coordinate plus the 1/8-cell sub-position (0..7) inside it
+__host__ __device__ __forceinline__ int cell_coord_fine(Real x, double o, double inv, int n, unsigned& sub)
+{
+    const double t = ((double)x - o) * inv;
+    const double fl = floor(t);
+    int c = (int)fl;
+    int s = (int)((t - fl) * 8.0);
+    if (c < 0) { c = 0; s = 0; }
+    if (c >= n) { c = n - 1; s = 7; }
+    sub = (unsigned)(s < 0 ? 0 : (s > 7 ? 7 : s));
+    return c;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ struct dfsph_b200_ctx {
     Real4 *acc = nullptr, *bgrad = nullptr;
     Real *density = nullptr, *factor = nullptr, *density_adv = nullptr;
     unsigned *nnbr = nullptr, *cnt_f = nullptr, *cnt_b = nullptr, *tab_f = nullptr, *tab_b = nullptr, *tcnt_f = nullptr, *tcnt_b = nullptr;
-    unsigned *cell_key = nullptr, *cell_rank = nullptr, *sorted_idx = nullptr;
+    unsigned *cell_key = nullptr, *cell_rank = nullptr, *cell_fine = nullptr, *sorted_idx = nullptr, *block_rank = nullptr;
     unsigned *cell_count = nullptr, *cell_start = nullptr, *scan_partial = nullptr;
     unsigned keys_cap = 0, scratch_cap = 0;
     bool tables_valid = false;   // neighbour table matches pos[cur_pos]
@@ -313,7 +313,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     }
     cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
     cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b); cudaFree(c->tcnt_f); cudaFree(c->tcnt_b);
-    cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
+    cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
     cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start);
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
@@ -359,6 +359,7 @@ static int ensure_scratch(dfsph_b200_ctx* c, unsigned count)
     if (count <= c->scratch_cap) return 0;
     if (dev_alloc(c, &c->cell_key, count)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->cell_rank, count)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->cell_fine, count)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->sorted_idx, count)) return DFSPH_B200_ERR_CUDA;
     c->scratch_cap = count;
     return 0;
@@ -390,6 +391,29 @@ static int setup_grid(dfsph_b200_ctx* c)
     const unsigned long long keys = (unsigned long long)nbx * nby * nbz * 512ull;
     if (keys > 1500000000ull) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "cell table too large (%llu cells)", keys);
     g.num_keys = (unsigned)keys;
+    {
+        // z-order over the blocks: rank of every block's Morton code (z most significant, like the in-block code)
+        const unsigned nblocks = nbx * nby * nbz;
+        auto spread10 = [](unsigned long long v) {
+            v &= 0x3ffull;
+            v = (v | (v << 16)) & 0x30000ffull;
+            v = (v | (v << 8)) & 0x300f00full;
+            v = (v | (v << 4)) & 0x30c30c3ull;
+            v = (v | (v << 2)) & 0x9249249ull;
+            return v;
+        };
+        std::vector<std::pair<unsigned long long, unsigned>> codes(nblocks);
+        for (unsigned bx = 0; bx < nbx; ++bx) for (unsigned by = 0; by < nby; ++by) for (unsigned bz = 0; bz < nbz; ++bz) {
+            const unsigned lin = (bx * nby + by) * nbz + bz;
+            codes[lin] = { spread10(bx) | (spread10(by) << 1) | (spread10(bz) << 2), lin };
+        }
+        std::sort(codes.begin(), codes.end());
+        std::vector<unsigned> rank(nblocks);
+        for (unsigned r = 0; r < nblocks; ++r) rank[codes[r].second] = r;
+        if (dev_alloc(c, &c->block_rank, nblocks)) return DFSPH_B200_ERR_CUDA;
+        CUDA_TRY(c, cudaMemcpy(c->block_rank, rank.data(), (size_t)nblocks * sizeof(unsigned), cudaMemcpyHostToDevice));
+        g.block_rank = c->block_rank;
+    }
     c->grid = g;
     if (g.num_keys + 1 > c->keys_cap) {
         if (dev_alloc(c, &c->cell_count, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
@@ -410,7 +434,7 @@ static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* 
     const GridDesc& g = c->grid;
     cudaStream_t st = c->stream;
     CUDA_TRY(c, cudaMemsetAsync(c->cell_count, 0, (size_t)g.num_keys * sizeof(unsigned), st));
-    if (n > 0) { k_cell_hash<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->cell_count, c->cell_key, c->cell_rank); c->launches++; }
+    if (n > 0) { k_cell_hash<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->cell_count, c->cell_key, c->cell_rank, c->cell_fine); c->launches++; }
     const unsigned nparts = div_up(g.num_keys, SCAN_CHUNK);
     k_scan_partials<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, g.num_keys, c->scan_partial);
     k_scan_spine<<<1, SCAN_BLOCK, 0, st>>>(c->scan_partial, nparts);
@@ -418,7 +442,7 @@ static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* 
     c->launches += 3;
     if (n > 0) {
         k_cell_scatter<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(c->cell_key, c->cell_rank, n, cell_start_out, c->sorted_idx);
-        k_cell_fix_order<<<div_up(g.num_keys, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(cell_start_out, g.num_keys, c->sorted_idx);
+        k_cell_fix_order<<<div_up(g.num_keys, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(cell_start_out, g.num_keys, c->cell_fine, c->sorted_idx);
         c->launches += 2;
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -105,16 +105,18 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const unsigned* __res
 // pos4.w is not used by the search.
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash(const Real4* __restrict__ pos, unsigned n, GridDesc g,
                                                              unsigned* __restrict__ cell_count, unsigned* __restrict__ key_out,
-                                                             unsigned* __restrict__ rank_out)
+                                                             unsigned* __restrict__ rank_out, unsigned* __restrict__ fine_out)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Real4 p = pos[i];
-    const int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
-    const int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
-    const int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+    unsigned sx, sy, sz;
+    const int cx = cell_coord_fine(p.x, g.ox, g.inv_cell, g.nx, sx);
+    const int cy = cell_coord_fine(p.y, g.oy, g.inv_cell, g.ny, sy);
+    const int cz = cell_coord_fine(p.z, g.oz, g.inv_cell, g.nz, sz);
     const unsigned key = cell_key(cx, cy, cz, g);
     key_out[i] = key;
+    fine_out[i] = spread3(sx) | (spread3(sy) << 1) | (spread3(sz) << 2);
     rank_out[i] = atomicAdd(cell_count + key, 1u);
 }
 
@@ -126,17 +128,25 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_scatter(const unsigned* __
     sorted_idx[cell_start[key[i]] + rank[i]] = i;
 }
 
-// The atomic ranks above depend on thread scheduling; sorting every cell segment by source index makes the
-// permutation (and with it every floating-point summation order downstream) reproducible run to run.
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_fix_order(const unsigned* __restrict__ cell_start, unsigned num_keys, unsigned* __restrict__ sorted_idx)
+// The atomic ranks above depend on thread scheduling.  Sorting every cell segment by (sub-cell Morton code, source
+// index) makes the permutation -- and with it every floating-point summation order downstream -- reproducible run to
+// run, and continues the z-order curve below the cell level.
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_fix_order(const unsigned* __restrict__ cell_start, unsigned num_keys,
+                                                                  const unsigned* __restrict__ fine, unsigned* __restrict__ sorted_idx)
 {
     const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= num_keys) return;
     const unsigned s = cell_start[c], e = cell_start[c + 1];
     for (unsigned a = s + 1; a < e; ++a) {
         const unsigned v = sorted_idx[a];
+        const unsigned long long kv = ((unsigned long long)fine[v] << 32) | v;
         unsigned b = a;
-        while (b > s && sorted_idx[b - 1] > v) { sorted_idx[b] = sorted_idx[b - 1]; --b; }
+        while (b > s) {
+            const unsigned w = sorted_idx[b - 1];
+            if ((((unsigned long long)fine[w] << 32) | w) <= kv) break;
+            sorted_idx[b] = w;
+            --b;
+        }
         sorted_idx[b] = v;
     }
 }
@@ -209,15 +219,16 @@ __device__ __forceinline__ unsigned search_cells(const Real4 xi, unsigned i, con
     const int cz = cell_coord(xi.z, g.oz, g.inv_cell, g.nz);
     unsigned cnt = 0;
     unsigned* my = tab + (size_t)tile * K * DFSPH_TILE + lane;
-    for (int dx = -1; dx <= 1; ++dx) {
-        const int x = cx + dx;
-        if (x < 0 || x >= g.nx) continue;
+    // z outermost / x innermost = ascending Morton order inside a block: lists come out (nearly) sorted by address
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int z = cz + dz;
+        if (z < 0 || z >= g.nz) continue;
         for (int dy = -1; dy <= 1; ++dy) {
             const int y = cy + dy;
             if (y < 0 || y >= g.ny) continue;
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int z = cz + dz;
-                if (z < 0 || z >= g.nz) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = cx + dx;
+                if (x < 0 || x >= g.nx) continue;
                 const unsigned key = cell_key(x, y, z, g);
                 const unsigned s = __ldg(other_cell_start + key), e = __ldg(other_cell_start + key + 1);
                 for (unsigned j = s; j < e; ++j) {
