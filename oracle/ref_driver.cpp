@@ -14,6 +14,7 @@
 #include "SPlisHSPlasH/BoundaryModel_Akinci2012.h"
 #include "SPlisHSPlasH/StaticRigidBody.h"
 #include "SPlisHSPlasH/DFSPH/TimeStepDFSPH.h"
+#include "TimeStepDFSPH_B200.h"   // the product's drop-in solver (splishsplash_b200/host), exercised through the reference stack
 #include "Utilities/Timing.h"
 #include "Utilities/Counting.h"
 #include "Utilities/Logger.h"
@@ -30,6 +31,7 @@ using namespace SPH;
 namespace {
 	double g_step_seconds = 0.0;
 	std::string g_err;
+	bool g_b200 = false;
 
 	const Real* fieldPtr(FluidModel* fm, const char* name, unsigned int i)
 	{
@@ -57,8 +59,10 @@ int ref_create(double particleRadius)
 {
 	if (Simulation::hasCurrent()) return -1;
 	Utilities::Timing::m_dontPrintTimes = true;
+	Simulation::setCurrent(new Simulation_B200());   // plain Simulation behaviour unless ref_configure_b200 is used
 	Simulation* sim = Simulation::getCurrent();
 	sim->init(static_cast<Real>(particleRadius), false);
+	g_b200 = false;
 	return 0;
 }
 
@@ -94,6 +98,26 @@ int ref_configure(int kernel, int gradKernel)
 	return 0;
 }
 
+/* Same configuration step, but the solver is the B200 drop-in (TimeStepDFSPH_B200 through Simulation_B200): the
+   reference's Simulation, FluidModel, BoundaryModel_Akinci2012 and TimeManager objects stay in charge of everything
+   else.  libdir: directory holding libdfsph_b200_*.so.  Returns -2 if the CUDA library / device is unavailable. */
+int ref_configure_b200(int kernel, int gradKernel, const char* libdir)
+{
+	Simulation* sim = Simulation::getCurrent();
+	sim->setValue<int>(Simulation::BOUNDARY_HANDLING_METHOD, Simulation::ENUM_AKINCI2012);
+	try {
+		static_cast<Simulation_B200*>(sim)->useB200Solver(libdir ? libdir : "");
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return -2;
+	}
+	sim->setValue<int>(Simulation::KERNEL_METHOD, kernel);
+	sim->setValue<int>(Simulation::GRAD_KERNEL_METHOD, gradKernel);
+	g_b200 = true;
+	return 0;
+}
+const char* ref_last_error() { return g_err.c_str(); }
+
 /* Static Akinci2012 boundary (StaticBoundarySimulator.cpp:146-152 + BoundaryModel_Akinci2012::initModel). */
 int ref_add_boundary(const Real* x, unsigned int n)
 {
@@ -124,11 +148,11 @@ int ref_finalize()
 int ref_set_real(const char* name, double v)
 {
 	Simulation* sim = Simulation::getCurrent();
-	TimeStepDFSPH* ts = static_cast<TimeStepDFSPH*>(sim->getTimeStep());
+	TimeStep* ts = sim->getTimeStep();
 	const std::string s(name);
 	if (s == "timeStepSize") TimeManager::getCurrent()->setTimeStepSize(static_cast<Real>(v));
-	else if (s == "maxError") ts->setValue<Real>(TimeStepDFSPH::MAX_ERROR, static_cast<Real>(v));
-	else if (s == "maxErrorV") ts->setValue<Real>(TimeStepDFSPH::MAX_ERROR_V, static_cast<Real>(v));
+	else if (s == "maxError") ts->setValue<Real>(g_b200 ? TimeStepDFSPH_B200::MAX_ERROR : TimeStepDFSPH::MAX_ERROR, static_cast<Real>(v));
+	else if (s == "maxErrorV") ts->setValue<Real>(g_b200 ? TimeStepDFSPH_B200::MAX_ERROR_V : TimeStepDFSPH::MAX_ERROR_V, static_cast<Real>(v));
 	else if (s == "cflFactor") sim->setValue<Real>(Simulation::CFL_FACTOR, static_cast<Real>(v));
 	else if (s == "cflMinTimeStepSize") sim->setValue<Real>(Simulation::CFL_MIN_TIMESTEPSIZE, static_cast<Real>(v));
 	else if (s == "cflMaxTimeStepSize") sim->setValue<Real>(Simulation::CFL_MAX_TIMESTEPSIZE, static_cast<Real>(v));
@@ -139,12 +163,12 @@ int ref_set_real(const char* name, double v)
 int ref_set_int(const char* name, int v)
 {
 	Simulation* sim = Simulation::getCurrent();
-	TimeStepDFSPH* ts = static_cast<TimeStepDFSPH*>(sim->getTimeStep());
+	TimeStep* ts = sim->getTimeStep();
 	const std::string s(name);
-	if (s == "minIterations") ts->setValue<unsigned int>(TimeStepDFSPH::MIN_ITERATIONS, (unsigned int)v);
-	else if (s == "maxIterations") ts->setValue<unsigned int>(TimeStepDFSPH::MAX_ITERATIONS, (unsigned int)v);
-	else if (s == "maxIterationsV") ts->setValue<unsigned int>(TimeStepDFSPH::MAX_ITERATIONS_V, (unsigned int)v);
-	else if (s == "enableDivergenceSolver") ts->setValue<bool>(TimeStepDFSPH::USE_DIVERGENCE_SOLVER, v != 0);
+	if (s == "minIterations") ts->setValue<unsigned int>(g_b200 ? TimeStepDFSPH_B200::MIN_ITERATIONS : TimeStepDFSPH::MIN_ITERATIONS, (unsigned int)v);
+	else if (s == "maxIterations") ts->setValue<unsigned int>(g_b200 ? TimeStepDFSPH_B200::MAX_ITERATIONS : TimeStepDFSPH::MAX_ITERATIONS, (unsigned int)v);
+	else if (s == "maxIterationsV") ts->setValue<unsigned int>(g_b200 ? TimeStepDFSPH_B200::MAX_ITERATIONS_V : TimeStepDFSPH::MAX_ITERATIONS_V, (unsigned int)v);
+	else if (s == "enableDivergenceSolver") ts->setValue<bool>(g_b200 ? TimeStepDFSPH_B200::USE_DIVERGENCE_SOLVER : TimeStepDFSPH::USE_DIVERGENCE_SOLVER, v != 0);
 	else if (s == "cflMethod") sim->setValue<int>(Simulation::CFL_METHOD, v);
 	else if (s == "enableZSort") sim->setValue<bool>(Simulation::ENABLE_Z_SORT, v != 0);
 	else if (s == "stepsPerZSort") sim->setValue<unsigned int>(Simulation::STEPS_PER_Z_SORT, (unsigned int)v);
@@ -197,8 +221,9 @@ unsigned int ref_num_particles(int fluid) { return Simulation::getCurrent()->get
 unsigned int ref_num_boundary_particles(int b) { return static_cast<BoundaryModel_Akinci2012*>(Simulation::getCurrent()->getBoundaryModel(b))->numberOfParticles(); }
 double ref_time() { return TimeManager::getCurrent()->getTime(); }
 double ref_time_step_size() { return TimeManager::getCurrent()->getTimeStepSize(); }
-int ref_iterations() { return Simulation::getCurrent()->getTimeStep()->getValue<unsigned int>(TimeStepDFSPH::SOLVER_ITERATIONS); }
-int ref_iterations_v() { return Simulation::getCurrent()->getTimeStep()->getValue<unsigned int>(TimeStepDFSPH::SOLVER_ITERATIONS_V); }
+int ref_iterations() { return Simulation::getCurrent()->getTimeStep()->getValue<unsigned int>(g_b200 ? TimeStepDFSPH_B200::SOLVER_ITERATIONS : TimeStepDFSPH::SOLVER_ITERATIONS); }
+int ref_iterations_v() { return Simulation::getCurrent()->getTimeStep()->getValue<unsigned int>(g_b200 ? TimeStepDFSPH_B200::SOLVER_ITERATIONS_V : TimeStepDFSPH::SOLVER_ITERATIONS_V); }
+const char* ref_method_name() { static std::string s; s = Simulation::getCurrent()->getTimeStep()->getMethodName(); return s.c_str(); }
 double ref_w_zero() { return Simulation::getCurrent()->W_zero(); }
 double ref_fluid_volume(int fluid) { return Simulation::getCurrent()->getFluidModel(fluid)->getVolume(0); }
 int ref_kernel() { return Simulation::getCurrent()->getKernel(); }

@@ -62,6 +62,10 @@ class RefSim:
         L.ref_neighbor_counts.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.ref_neighbor_lists.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_set_num_threads.argtypes = [C.c_int]
+        if hasattr(L, "ref_configure_b200"):   # only the reference build carries the drop-in solver
+            L.ref_configure_b200.argtypes = [C.c_int, C.c_int, C.c_char_p]
+            L.ref_last_error.restype = C.c_char_p
+            L.ref_method_name.restype = C.c_char_p
         assert L.ref_sizeof_real() == np.dtype(self.dtype).itemsize
         self._alive = False
         self.n_fluid_models = 0
@@ -85,6 +89,17 @@ class RefSim:
 
     def configure(self, kernel=4, grad_kernel=None):
         self.lib.ref_configure(int(kernel), int(kernel if grad_kernel is None else grad_kernel))
+
+    def configure_b200(self, kernel=4, libdir=None):
+        """Install the product's C++ drop-in TimeStepDFSPH_B200 as the solver of the reference Simulation."""
+        libdir = libdir or os.path.join(os.path.dirname(_HERE), "splishsplash_b200")
+        rc = self.lib.ref_configure_b200(int(kernel), int(kernel), libdir.encode())
+        if rc != 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+
+    @property
+    def method_name(self):
+        return self.lib.ref_method_name().decode()
 
     def add_boundary(self, x):
         x = np.ascontiguousarray(x, dtype=self.dtype)
@@ -208,12 +223,16 @@ class RefSim:
         self.destroy()
 
 
-def build_ref_scene(scene, precision="f64", kernel=4, lib_path=None, **params):
-    """Create a RefSim for a ``splishsplash_b200.scenes`` scene dict."""
+def build_ref_scene(scene, precision="f64", kernel=4, lib_path=None, b200=False, **params):
+    """Create a RefSim for a ``splishsplash_b200.scenes`` scene dict.  b200=True swaps the reference's TimeStepDFSPH
+    for the drop-in TimeStepDFSPH_B200 (everything else stays the reference's own code)."""
     sim = RefSim(precision, lib_path)
     sim.create(scene["radius"])
     sim.add_fluid(scene["fluid_x"], scene.get("fluid_v"))
-    sim.configure(kernel)
+    if b200:
+        sim.configure_b200(kernel)
+    else:
+        sim.configure(kernel)
     if scene.get("boundary_x") is not None and len(scene["boundary_x"]):
         sim.add_boundary(scene["boundary_x"])
     if params:

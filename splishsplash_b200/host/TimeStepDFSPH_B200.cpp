@@ -1,0 +1,307 @@
+#include "TimeStepDFSPH_B200.h"
+#include "dfsph_b200.h"
+#include "SPlisHSPlasH/TimeManager.h"
+#include "SPlisHSPlasH/BoundaryModel_Akinci2012.h"
+#include "Utilities/Timing.h"
+#include "Utilities/Counting.h"
+#include "Utilities/Logger.h"
+#include <dlfcn.h>
+#include <cstdlib>
+#include <stdexcept>
+
+using namespace SPH;
+using namespace GenParam;
+
+std::string TimeStepDFSPH_B200::METHOD_NAME = "DFSPH_B200";
+int TimeStepDFSPH_B200::SOLVER_ITERATIONS = -1;
+int TimeStepDFSPH_B200::MIN_ITERATIONS = -1;
+int TimeStepDFSPH_B200::MAX_ITERATIONS = -1;
+int TimeStepDFSPH_B200::MAX_ERROR = -1;
+int TimeStepDFSPH_B200::SOLVER_ITERATIONS_V = -1;
+int TimeStepDFSPH_B200::MAX_ITERATIONS_V = -1;
+int TimeStepDFSPH_B200::MAX_ERROR_V = -1;
+int TimeStepDFSPH_B200::USE_DIVERGENCE_SOLVER = -1;
+
+// function table resolved from the shared object (the binding a maintainer adds: see INTEGRATION.md)
+struct TimeStepDFSPH_B200::Api
+{
+	decltype(&dfsph_b200_sizeof_real) sizeof_real;
+	decltype(&dfsph_b200_default_config) default_config;
+	decltype(&dfsph_b200_default_params) default_params;
+	decltype(&dfsph_b200_create) create;
+	decltype(&dfsph_b200_destroy) destroy;
+	decltype(&dfsph_b200_last_error) last_error;
+	decltype(&dfsph_b200_set_fluid) set_fluid;
+	decltype(&dfsph_b200_add_boundary) add_boundary;
+	decltype(&dfsph_b200_set_params) set_params;
+	decltype(&dfsph_b200_step_host) step_host;
+	decltype(&dfsph_b200_download) download;
+};
+
+template <typename F>
+static void resolve(void* lib, F& fn, const char* name)
+{
+	fn = reinterpret_cast<F>(dlsym(lib, name));
+	if (!fn) throw std::runtime_error(std::string("TimeStepDFSPH_B200: symbol missing in CUDA library: ") + name);
+}
+
+void TimeStepDFSPH_B200::loadLibrary(const std::string& path)
+{
+	const std::string name = sizeof(Real) == 8 ? "libdfsph_b200_f64.so" : "libdfsph_b200_f32.so";
+	std::string dir = path;
+	if (dir.empty() && std::getenv("DFSPH_B200_LIB_DIR")) dir = std::getenv("DFSPH_B200_LIB_DIR");
+	const std::string full = dir.empty() ? name : dir + "/" + name;
+	m_lib = dlopen(full.c_str(), RTLD_NOW | RTLD_LOCAL);
+	if (!m_lib) throw std::runtime_error("TimeStepDFSPH_B200: cannot load " + full + ": " + dlerror() + " (no CPU fallback)");
+	m_api = new Api();
+	resolve(m_lib, m_api->sizeof_real, "dfsph_b200_sizeof_real");
+	resolve(m_lib, m_api->default_config, "dfsph_b200_default_config");
+	resolve(m_lib, m_api->default_params, "dfsph_b200_default_params");
+	resolve(m_lib, m_api->create, "dfsph_b200_create");
+	resolve(m_lib, m_api->destroy, "dfsph_b200_destroy");
+	resolve(m_lib, m_api->last_error, "dfsph_b200_last_error");
+	resolve(m_lib, m_api->set_fluid, "dfsph_b200_set_fluid");
+	resolve(m_lib, m_api->add_boundary, "dfsph_b200_add_boundary");
+	resolve(m_lib, m_api->set_params, "dfsph_b200_set_params");
+	resolve(m_lib, m_api->step_host, "dfsph_b200_step_host");
+	resolve(m_lib, m_api->download, "dfsph_b200_download");
+	if (m_api->sizeof_real() != (int)sizeof(Real)) throw std::runtime_error("TimeStepDFSPH_B200: Real size mismatch between the reference build and " + full);
+}
+
+void TimeStepDFSPH_B200::check(int rc, const char* what)
+{
+	if (rc == 0) return;
+	const std::string msg = std::string("TimeStepDFSPH_B200: ") + what + " failed (" + std::to_string(rc) + "): " + m_api->last_error(m_ctx);
+	LOG_ERR << msg;
+	throw std::runtime_error(msg);
+}
+
+TimeStepDFSPH_B200::TimeStepDFSPH_B200(const std::string& libraryPath) :
+	TimeStep(), m_lib(nullptr), m_ctx(nullptr), m_modelUploaded(false), m_api(nullptr)
+{
+	// defaults of TimeStepDFSPH (TimeStepDFSPH.cpp:33-41)
+	m_iterations = 0;
+	m_minIterations = 2;
+	m_maxIterations = 100;
+	m_maxError = static_cast<Real>(0.01);
+	m_iterationsV = 0;
+	m_enableDivergenceSolver = true;
+	m_maxIterationsV = 100;
+	m_maxErrorV = static_cast<Real>(0.1);
+	m_syncAllFields = true;
+
+	loadLibrary(libraryPath);
+	resize();
+
+	// the same particle fields as TimeStepDFSPH (TimeStepDFSPH.cpp:44-54), served from the host mirrors
+	Simulation* sim = Simulation::getCurrent();
+	if (sim->numberOfFluidModels() > 0)
+	{
+		FluidModel* model = sim->getFluidModel(0);
+		model->addField({ "factor", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_factor[i]; } });
+		model->addField({ "advected density", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_density_adv[i]; } });
+		model->addField({ "p / rho^2", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_pressure_rho2[i]; }, true });
+		model->addField({ "p_v / rho^2", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_pressure_rho2_V[i]; }, true });
+		model->addField({ "pressure acceleration", METHOD_NAME, FieldType::Vector3, [this](const unsigned int i) -> Real* { return &m_pressureAccel[i][0]; } });
+	}
+}
+
+TimeStepDFSPH_B200::~TimeStepDFSPH_B200(void)
+{
+	Simulation* sim = Simulation::getCurrent();
+	if (sim->numberOfFluidModels() > 0)
+	{
+		FluidModel* model = sim->getFluidModel(0);
+		model->removeFieldByName("factor");
+		model->removeFieldByName("advected density");
+		model->removeFieldByName("p / rho^2");
+		model->removeFieldByName("p_v / rho^2");
+		model->removeFieldByName("pressure acceleration");
+	}
+	if (m_ctx) m_api->destroy(m_ctx);
+	delete m_api;
+	if (m_lib) dlclose(m_lib);
+}
+
+void TimeStepDFSPH_B200::initParameters()
+{
+	TimeStep::initParameters();
+
+	// identical names, groups and limits to TimeStepDFSPH::initParameters (TimeStepDFSPH.cpp:73-115)
+	SOLVER_ITERATIONS = createNumericParameter("iterations", "Iterations", &m_iterations);
+	setGroup(SOLVER_ITERATIONS, "Simulation|DFSPH");
+	setDescription(SOLVER_ITERATIONS, "Iterations required by the pressure solver.");
+	getParameter(SOLVER_ITERATIONS)->setReadOnly(true);
+
+	MIN_ITERATIONS = createNumericParameter("minIterations", "Min. iterations", &m_minIterations);
+	setGroup(MIN_ITERATIONS, "Simulation|DFSPH");
+	setDescription(MIN_ITERATIONS, "Minimal number of iterations of the pressure solver.");
+	static_cast<NumericParameter<unsigned int>*>(getParameter(MIN_ITERATIONS))->setMinValue(0);
+
+	MAX_ITERATIONS = createNumericParameter("maxIterations", "Max. iterations", &m_maxIterations);
+	setGroup(MAX_ITERATIONS, "Simulation|DFSPH");
+	setDescription(MAX_ITERATIONS, "Maximal number of iterations of the pressure solver.");
+	static_cast<NumericParameter<unsigned int>*>(getParameter(MAX_ITERATIONS))->setMinValue(1);
+
+	MAX_ERROR = createNumericParameter("maxError", "Max. density error(%)", &m_maxError);
+	setGroup(MAX_ERROR, "Simulation|DFSPH");
+	setDescription(MAX_ERROR, "Maximal density error (%).");
+	static_cast<RealParameter*>(getParameter(MAX_ERROR))->setMinValue(static_cast<Real>(1e-6));
+
+	SOLVER_ITERATIONS_V = createNumericParameter("iterationsV", "Iterations (divergence)", &m_iterationsV);
+	setGroup(SOLVER_ITERATIONS_V, "Simulation|DFSPH");
+	setDescription(SOLVER_ITERATIONS_V, "Iterations required by the divergence solver.");
+	getParameter(SOLVER_ITERATIONS_V)->setReadOnly(true);
+
+	MAX_ITERATIONS_V = createNumericParameter("maxIterationsV", "Max. iterations (divergence)", &m_maxIterationsV);
+	setGroup(MAX_ITERATIONS_V, "Simulation|DFSPH");
+	setDescription(MAX_ITERATIONS_V, "Maximal number of iterations of the divergence solver.");
+	static_cast<NumericParameter<unsigned int>*>(getParameter(MAX_ITERATIONS_V))->setMinValue(1);
+
+	MAX_ERROR_V = createNumericParameter("maxErrorV", "Max. divergence error(%)", &m_maxErrorV);
+	setGroup(MAX_ERROR_V, "Simulation|DFSPH");
+	setDescription(MAX_ERROR_V, "Maximal divergence error (%).");
+	static_cast<RealParameter*>(getParameter(MAX_ERROR_V))->setMinValue(static_cast<Real>(1e-6));
+
+	USE_DIVERGENCE_SOLVER = createBoolParameter("enableDivergenceSolver", "Enable divergence solver", &m_enableDivergenceSolver);
+	setGroup(USE_DIVERGENCE_SOLVER, "Simulation|DFSPH");
+	setDescription(USE_DIVERGENCE_SOLVER, "Turn divergence solver on/off.");
+}
+
+void TimeStepDFSPH_B200::resize()
+{
+	// SimulationDataDFSPH::init (SimulationDataDFSPH.cpp:22-42): size the per-particle arrays from the fluid models
+	Simulation* sim = Simulation::getCurrent();
+	if (sim->numberOfFluidModels() > 1)
+		throw std::runtime_error("TimeStepDFSPH_B200: multiphase scenes (more than one fluid model) are outside the B200 hot-path scope");
+	if (sim->is2DSimulation())
+		throw std::runtime_error("TimeStepDFSPH_B200: 2-D simulations are outside the B200 hot-path scope");
+	const unsigned int n = sim->numberOfFluidModels() ? sim->getFluidModel(0)->numParticles() : 0;
+	m_factor.assign(n, 0.0);
+	m_density_adv.assign(n, 0.0);
+	m_pressure_rho2.assign(n, 0.0);
+	m_pressure_rho2_V.assign(n, 0.0);
+	m_pressureAccel.assign(n, Vector3r::Zero());
+	m_modelUploaded = false;
+}
+
+void TimeStepDFSPH_B200::reset()
+{
+	TimeStep::reset();
+	resize();          // SimulationDataDFSPH::reset zeroes the warm-start values
+	m_iterations = 0;
+	m_iterationsV = 0;
+}
+
+void TimeStepDFSPH_B200::pushParameters()
+{
+	Simulation* sim = Simulation::getCurrent();
+	dfsph_b200_params p;
+	m_api->default_params(&p);
+	p.time_step_size = TimeManager::getCurrent()->getTimeStepSize();
+	const Real* g = sim->getVecValue<Real>(Simulation::GRAVITATION);
+	for (int k = 0; k < 3; k++) p.gravitation[k] = g[k];
+	p.min_iterations = m_minIterations;
+	p.max_iterations = m_maxIterations;
+	p.max_error = m_maxError;
+	p.max_iterations_v = m_maxIterationsV;
+	p.max_error_v = m_maxErrorV;
+	p.enable_divergence_solver = m_enableDivergenceSolver ? 1 : 0;
+	p.cfl_method = sim->getValue<int>(Simulation::CFL_METHOD);
+	p.cfl_factor = sim->getValue<Real>(Simulation::CFL_FACTOR);
+	p.cfl_min_time_step_size = sim->getValue<Real>(Simulation::CFL_MIN_TIMESTEPSIZE);
+	p.cfl_max_time_step_size = sim->getValue<Real>(Simulation::CFL_MAX_TIMESTEPSIZE);
+	check(m_api->set_params(m_ctx, &p), "dfsph_b200_set_params");
+}
+
+void TimeStepDFSPH_B200::uploadModel()
+{
+	Simulation* sim = Simulation::getCurrent();
+	if (sim->getBoundaryHandlingMethod() != BoundaryHandlingMethods::Akinci2012 && sim->numberOfBoundaryModels() > 0)
+		throw std::runtime_error("TimeStepDFSPH_B200: only boundaryHandlingMethod 0 (Akinci2012) is supported on the B200 path");
+	FluidModel* fm = sim->getFluidModel(0);
+	if (fm->getViscosityMethod() != 0 || fm->getVorticityMethod() != 0 || fm->getDragMethod() != 0 ||
+		fm->getSurfaceTensionMethod() != 0 || fm->getElasticityMethod() != 0)
+		throw std::runtime_error("TimeStepDFSPH_B200: non-pressure forces run on the host in the reference; set viscosityMethod/"
+			"vorticityMethod/dragMethod/surfaceTensionMethod/elasticityMethod to 0 for the B200 path (SURVEY.md H6)");
+
+	if (m_ctx) { m_api->destroy(m_ctx); m_ctx = nullptr; }
+	dfsph_b200_config cfg;
+	m_api->default_config(&cfg);
+	cfg.particle_radius = sim->getParticleRadius();
+	cfg.kernel = sim->getKernel();      // 0 cubic / 4 precomputed cubic (Simulation.cpp:215-253)
+	if (const char* dev = std::getenv("DFSPH_B200_DEVICE")) cfg.device = std::atoi(dev);
+	check(m_api->create(&cfg, &m_ctx), "dfsph_b200_create");
+	pushParameters();
+
+	const unsigned int n = fm->numActiveParticles();
+	std::vector<unsigned int> state(n);
+	for (unsigned int i = 0; i < n; i++) state[i] = static_cast<unsigned int>(fm->getParticleState(i));
+	// host array index is the particle identity on the device side (row k of every by-id transfer = host slot k)
+	check(m_api->set_fluid(m_ctx, n, n ? &fm->getPosition(0)[0] : nullptr, n ? &fm->getVelocity(0)[0] : nullptr, nullptr,
+		state.data(), fm->getDensity0(), fm->getVolume(0)), "dfsph_b200_set_fluid");
+
+	for (unsigned int b = 0; b < sim->numberOfBoundaryModels(); b++)
+	{
+		BoundaryModel_Akinci2012* bm = static_cast<BoundaryModel_Akinci2012*>(sim->getBoundaryModel(b));
+		const bool dynamic = bm->getRigidBodyObject()->isDynamic() || bm->getRigidBodyObject()->isAnimated();
+		const unsigned int nb = bm->numberOfParticles();
+		check(m_api->add_boundary(m_ctx, nb, nb ? &bm->getPosition(0)[0] : nullptr, nb ? &bm->getVolume(0) : nullptr, dynamic ? 1 : 0),
+			"dfsph_b200_add_boundary");
+	}
+	m_modelUploaded = true;
+}
+
+void TimeStepDFSPH_B200::step()
+{
+	Simulation* sim = Simulation::getCurrent();
+	TimeManager* tm = TimeManager::getCurrent();
+	const Real h = tm->getTimeStepSize();
+	if (sim->numberOfFluidModels() == 0) { tm->setTime(tm->getTime() + h); return; }
+	FluidModel* fm = sim->getFluidModel(0);
+
+	if (!m_modelUploaded) uploadModel();
+	pushParameters();
+
+	// search + density + factor + divergence solve + CFL + pressure solve + advection, one call
+	START_TIMING("DFSPH_B200 step");
+	dfsph_b200_step_stats stats;
+	const unsigned int n = fm->numActiveParticles();
+	check(m_api->step_host(m_ctx, n ? &fm->getPosition(0)[0] : nullptr, n ? &fm->getVelocity(0)[0] : nullptr,
+		n ? &fm->getDensity(0) : nullptr, &stats), "dfsph_b200_step_host");
+	STOP_TIMING_AVG;
+
+	m_iterations = stats.iterations;
+	m_iterationsV = m_enableDivergenceSolver ? stats.iterations_v : 0;
+	INCREASE_COUNTER("DFSPH - iterations", static_cast<Real>(m_iterations));      // TimeStepDFSPH.cpp:343
+	if (m_enableDivergenceSolver)
+		INCREASE_COUNTER("DFSPH - iterationsV", static_cast<Real>(m_iterationsV)); // :497
+
+	if (m_syncAllFields && n > 0)
+	{
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_FACTOR, m_factor.data(), n * sizeof(Real), 1), "download factor");
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_DENSITY_ADV, m_density_adv.data(), n * sizeof(Real), 1), "download advected density");
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_KAPPA, m_pressure_rho2.data(), n * sizeof(Real), 1), "download p / rho^2");
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_KAPPA_V, m_pressure_rho2_V.data(), n * sizeof(Real), 1), "download p_v / rho^2");
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_PRESSURE_ACCEL, &m_pressureAccel[0][0], n * 3 * sizeof(Real), 1), "download pressure acceleration");
+	}
+
+	// Simulation::updateTimeStepSize ran on the device (Simulation.cpp:395-493); publish its result, then advance time
+	// with the step's initial h exactly like TimeStepDFSPH::step (:248)
+	tm->setTimeStepSize(static_cast<Real>(stats.time_step_size));
+	tm->setTime(tm->getTime() + h);
+}
+
+void Simulation_B200::useB200Solver(const std::string& libraryPath)
+{
+	// what Simulation::setSimulationMethod does for every built-in method (Simulation.cpp:544-601)
+	delete m_timeStep;
+	m_timeStep = nullptr;
+	m_simulationMethod = SimulationMethods::NumSimulationMethods;
+	m_timeStep = new TimeStepDFSPH_B200(libraryPath);
+	m_timeStep->init();
+	setValue(Simulation::KERNEL_METHOD, Simulation::ENUM_KERNEL_PRECOMPUTED_CUBIC);
+	setValue(Simulation::GRAD_KERNEL_METHOD, Simulation::ENUM_GRADKERNEL_PRECOMPUTED_CUBIC);
+	if (m_simulationMethodChanged != nullptr)
+		m_simulationMethodChanged();
+}

@@ -1,0 +1,52 @@
+"""GPU test of the drop-in boundary: the reference's OWN Simulation / FluidModel / BoundaryModel_Akinci2012 /
+TimeManager objects (compiled unmodified into oracle/_ref) run with the product's C++ solver class
+TimeStepDFSPH_B200 (splishsplash_b200/host) installed in place of TimeStepDFSPH, and the result is compared with the
+same stack running the reference's TimeStepDFSPH.  Skipped where oracle/_ref is not present."""
+import numpy as np
+import pytest
+
+from oracle import refsim
+from splishsplash_b200 import scenes
+from tests.parity import TOL, conditioned_errors, dtype_of, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(scene, prec, b200, steps):
+    sim = refsim.build_ref_scene(scene, prec, kernel=4, b200=b200)
+    out = []
+    try:
+        name = sim.method_name
+        for _ in range(steps):
+            sim.step(1)
+            out.append({"iters": (sim.iterations_v, sim.iterations), "h": sim.h, "time": sim.time,
+                        **{f: sim.field_by_id(f) for f in ("position", "velocity", "density", "factor", "p / rho^2",
+                                                           "p_v / rho^2", "advected density")}})
+    finally:
+        sim.destroy()
+    return name, out
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_reference_stack_with_b200_solver(prec):
+    if not refsim.ref_available(prec):
+        pytest.skip("oracle/_ref not present")
+    sc = scenes.dam_break("small", dtype=dtype_of(prec))
+    steps = 4   # free-running from the same initial state; short enough that rounding differences stay below tolerance
+    name_ref, ref = _run(sc, prec, False, steps)
+    name_dev, dev = _run(sc, prec, True, steps)
+    assert name_ref == "DFSPH" and name_dev == "DFSPH_B200"
+    tol = TOL[prec] * (1 if prec == "f64" else 4)   # float: four free-running steps accumulate rounding differences
+    for s in range(steps):
+        assert ref[s]["iters"] == dev[s]["iters"]
+        assert abs(ref[s]["h"] - dev[s]["h"]) <= tol * ref[s]["h"]
+        assert abs(ref[s]["time"] - dev[s]["time"]) <= 1e-6 * max(ref[s]["time"], 1e-3)
+        for f in ("position", "velocity", "density", "factor", "advected density", "p_v / rho^2"):
+            assert scaled_err(dev[s][f], ref[s][f]) <= tol, (s, f)
+        e = scaled_err(dev[s]["p / rho^2"], ref[s]["p / rho^2"])
+        if e > tol:
+            h = ref[s]["h"]
+            d = np.abs(dev[s]["p / rho^2"].astype(np.float64) - ref[s]["p / rho^2"].astype(np.float64))
+            alpha = ref[s]["factor"].astype(np.float64) * h * h
+            e = float(np.max(d[alpha > 0] / alpha[alpha > 0]))
+        assert e <= tol, (s, "p / rho^2", e)
