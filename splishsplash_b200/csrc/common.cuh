@@ -141,7 +141,8 @@ struct Ctrl {
     unsigned overflow;      // neighbour-table capacity exceeded (value = needed capacity)
     unsigned overflow_b;
     unsigned max_nbr;
-    unsigned pad;
+    unsigned multi;         // 1: multi-GPU run, loop control happens in k_solve_control after the all-reduce
+    unsigned long long n_global;   // particles of all ranks (divisor of the average density error)
 };
 
 struct SolverParams {

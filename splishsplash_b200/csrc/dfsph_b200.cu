@@ -5,6 +5,7 @@
 #include "sph_kernels.cuh"
 #include "search_kernels.cuh"
 #include "solver_kernels.cuh"
+#include "multi_gpu.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +75,21 @@ struct dfsph_b200_ctx {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     void* stage = nullptr;       // device staging for AoS transfers
     size_t stage_bytes = 0;
+
+    // multi-GPU slab decomposition (csrc/multi_gpu.cuh)
+    bool multi = false;
+    int rank = 0, world = 1;
+    bool has_left = false, has_right = false;
+    double slab_lo = -1e300, slab_hi = 1e300;
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    unsigned ghost_cap = 0, ng = 0, ng_l = 0, ng_r = 0, n_exp_l = 0, n_exp_r = 0;
+    unsigned *exp_l = nullptr, *exp_r = nullptr, *gcell_start = nullptr;
+    Real4 *send_l = nullptr, *send_r = nullptr, *send_l2 = nullptr, *send_r2 = nullptr;
+    MigrantAux *aux_sl = nullptr, *aux_sr = nullptr, *aux_rl = nullptr, *aux_rr = nullptr;
+    ExchangeCounts* xcnt = nullptr;       // device: [0] mine, [1] from left, [2] from right
+    ExchangeCounts* h_xcnt = nullptr;     // pinned mirror
+    unsigned migrated_in = 0, migrated_out = 0;
 
     // optional per-kernel-class device timing (CUDA events on the launching stream)
     bool profiling = false;
@@ -316,6 +332,11 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
     cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start);
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
+    cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->send_l); cudaFree(c->send_r);
+    cudaFree(c->send_l2); cudaFree(c->send_r2); cudaFree(c->aux_sl); cudaFree(c->aux_sr); cudaFree(c->aux_rl); cudaFree(c->aux_rr);
+    cudaFree(c->xcnt);
+    if (c->h_xcnt) cudaFreeHost(c->h_xcnt);
+    if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
     for (int k = 0; k < 3; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
     for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -419,7 +440,8 @@ static int setup_grid(dfsph_b200_ctx* c)
         if (dev_alloc(c, &c->cell_count, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->cell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->bcell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
-        if (dev_alloc(c, &c->scan_partial, div_up(g.num_keys, SCAN_CHUNK) + 8)) return DFSPH_B200_ERR_CUDA;
+        if (c->multi && dev_alloc(c, &c->gcell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->scan_partial, div_up(g.num_keys + 1, SCAN_CHUNK) + 8)) return DFSPH_B200_ERR_CUDA;
         c->keys_cap = g.num_keys + 1;
     }
     c->grid_valid = true;
@@ -429,20 +451,27 @@ static int setup_grid(dfsph_b200_ctx* c)
 }
 
 // counting sort of `n` points at `pos` into the cell table `cell_start_out`; leaves the permutation in sorted_idx
-static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* cell_start_out)
+// slab: particles outside the context's slab are filed under the dump key num_keys (multi-GPU migration)
+static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* cell_start_out, bool slab = false)
 {
     const GridDesc& g = c->grid;
     cudaStream_t st = c->stream;
-    CUDA_TRY(c, cudaMemsetAsync(c->cell_count, 0, (size_t)g.num_keys * sizeof(unsigned), st));
-    if (n > 0) { k_cell_hash<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->cell_count, c->cell_key, c->cell_rank, c->cell_fine); c->launches++; }
-    const unsigned nparts = div_up(g.num_keys, SCAN_CHUNK);
-    k_scan_partials<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, g.num_keys, c->scan_partial);
+    const unsigned nk = g.num_keys + 1u;   // + dump cell
+    CUDA_TRY(c, cudaMemsetAsync(c->cell_count, 0, (size_t)nk * sizeof(unsigned), st));
+    if (n > 0) {
+        if (slab) k_cell_hash_slab<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->slab_lo, c->slab_hi, c->has_left, c->has_right,
+                                                                                   c->cell_count, c->cell_key, c->cell_rank, c->cell_fine);
+        else k_cell_hash<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->cell_count, c->cell_key, c->cell_rank, c->cell_fine);
+        c->launches++;
+    }
+    const unsigned nparts = div_up(nk, SCAN_CHUNK);
+    k_scan_partials<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, nk, c->scan_partial);
     k_scan_spine<<<1, SCAN_BLOCK, 0, st>>>(c->scan_partial, nparts);
-    k_scan_apply<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, g.num_keys, c->scan_partial, nparts, cell_start_out);
+    k_scan_apply<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, nk, c->scan_partial, nparts, cell_start_out);
     c->launches += 3;
     if (n > 0) {
         k_cell_scatter<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(c->cell_key, c->cell_rank, n, cell_start_out, c->sorted_idx);
-        k_cell_fix_order<<<div_up(g.num_keys, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(cell_start_out, g.num_keys, c->cell_fine, c->sorted_idx);
+        k_cell_fix_order<<<div_up(nk, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(cell_start_out, nk, c->cell_fine, c->sorted_idx);
         c->launches += 2;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -493,15 +522,33 @@ static int finalize_boundary(dfsph_b200_ctx* c)
 
 static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
 {
+    if (c->multi) {
+        // room for one support radius of ghosts per face plus migrants; generous: an eighth of the slab, >= 256 Ki
+        c->ghost_cap = std::max(cap / 8u, 262144u);
+        const unsigned gc = c->ghost_cap;
+        if (dev_alloc(c, &c->exp_l, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->exp_r, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->send_l, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->send_r, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->send_l2, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->send_r2, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->aux_sl, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->aux_sr, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->aux_rl, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->aux_rr, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->xcnt, 3)) return DFSPH_B200_ERR_CUDA;
+        if (!c->h_xcnt) CUDA_TRY(c, cudaMallocHost((void**)&c->h_xcnt, 3 * sizeof(ExchangeCounts)));
+        cap += gc;   // owned capacity includes room for arrivals
+    }
     for (int k = 0; k < 2; ++k) {
-        if (dev_alloc(c, &c->pos[k], cap + 1)) return DFSPH_B200_ERR_CUDA;   // +1: sentinel particle
-        if (dev_alloc(c, &c->vel[k], cap + 1)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->pos[k], cap + c->ghost_cap + 1)) return DFSPH_B200_ERR_CUDA;   // ghosts, then the sentinel particle
+        if (dev_alloc(c, &c->vel[k], cap + c->ghost_cap + 1)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->kappa[k], cap)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->kappa_v[k], cap)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->id[k], cap)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->state[k], cap)) return DFSPH_B200_ERR_CUDA;
     }
-    if (dev_alloc(c, &c->acc, cap + 1)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->acc, cap + c->ghost_cap + 1)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->bgrad, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->density, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->factor, cap)) return DFSPH_B200_ERR_CUDA;
@@ -607,6 +654,8 @@ int dfsph_b200_set_fluid(dfsph_b200_ctx* c, uint64_t n64, const void* x_, const 
     memset(&hc, 0, sizeof(hc));
     hc.h = (Real)c->par.time_step_size;
     hc.h_step = hc.h;
+    hc.multi = c->multi ? 1u : 0u;
+    hc.n_global = n;
     CUDA_TRY(c, cudaMemcpy(c->ctrl, &hc, sizeof(hc), cudaMemcpyHostToDevice));
     c->grid_valid = false;
     c->tables_valid = false;
@@ -717,25 +766,147 @@ static FluidArrays fluid_arrays(dfsph_b200_ctx* c)
     return f;
 }
 
+#define NCCL_TRY(ctx, expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) { (ctx)->sticky = 1; \
+    CTX_FAIL(ctx, DFSPH_B200_ERR_COMM, "%s failed: %s", #expr, (ctx)->nccl.GetErrorString(_r)); } } while (0)
+
+// exchange the per-rank counters with both slab neighbours and bring all three to the host (one synchronisation)
+static int exchange_counts(dfsph_b200_ctx* c)
+{
+    cudaStream_t st = c->stream;
+    const size_t b = sizeof(ExchangeCounts);
+    CUDA_TRY(c, cudaMemsetAsync(c->xcnt + 1, 0, 2 * b, st));
+    NCCL_TRY(c, c->nccl.GroupStart());
+    if (c->has_left) { NCCL_TRY(c, c->nccl.Send(c->xcnt, b, ncclChar, c->rank - 1, c->comm, st)); NCCL_TRY(c, c->nccl.Recv(c->xcnt + 1, b, ncclChar, c->rank - 1, c->comm, st)); }
+    if (c->has_right) { NCCL_TRY(c, c->nccl.Send(c->xcnt, b, ncclChar, c->rank + 1, c->comm, st)); NCCL_TRY(c, c->nccl.Recv(c->xcnt + 2, b, ncclChar, c->rank + 1, c->comm, st)); }
+    NCCL_TRY(c, c->nccl.GroupEnd());
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_xcnt, c->xcnt, 3 * b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// refresh one Real4 field of the ghost particles from the owning ranks (ghost slots [n, n+ng) of `arr`)
+static int exchange_ghosts(dfsph_b200_ctx* c, Real4* arr)
+{
+    if (!c->multi) return 0;
+    cudaStream_t st = c->stream;
+    const unsigned tot = c->n_exp_l + c->n_exp_r;
+    if (tot > 0) { k_pack_exports<<<div_up(tot, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(arr, c->exp_l, c->n_exp_l, c->exp_r, c->n_exp_r, c->send_l, c->send_r); c->launches++; }
+    const size_t e = sizeof(Real4);
+    NCCL_TRY(c, c->nccl.GroupStart());
+    if (c->has_left) {
+        NCCL_TRY(c, c->nccl.Send(c->send_l, (size_t)c->n_exp_l * e, ncclChar, c->rank - 1, c->comm, st));
+        NCCL_TRY(c, c->nccl.Recv(arr + c->n, (size_t)c->ng_l * e, ncclChar, c->rank - 1, c->comm, st));
+    }
+    if (c->has_right) {
+        NCCL_TRY(c, c->nccl.Send(c->send_r, (size_t)c->n_exp_r * e, ncclChar, c->rank + 1, c->comm, st));
+        NCCL_TRY(c, c->nccl.Recv(arr + c->n + c->ng_l, (size_t)c->ng_r * e, ncclChar, c->rank + 1, c->comm, st));
+    }
+    NCCL_TRY(c, c->nccl.GroupEnd());
+    return 0;
+}
+
 // Simulation::performNeighborhoodSearch: sort + reorder + neighbour table
 static int run_search(dfsph_b200_ctx* c)
 {
-    const unsigned n = c->n;
     cudaStream_t st = c->stream;
+    unsigned n = c->n;
     int rc;
-    { ProfScope ps(c, DFSPH_B200_PROF_SORT); rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start); }
-    if (rc) return rc;
+    if (c->multi) {
+        // ---- particle migration: owned particles that left the slab go to the neighbour rank --------------------------
+        k_zero_counts<<<1, 1, 0, st>>>(c->xcnt);
+        if (n > 0) k_pack_leavers<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->pos[c->cur_pos], c->vel[c->cur], c->kappa[c->cur], c->kappa_v[c->cur],
+            c->id[c->cur], c->state[c->cur], c->slab_lo, c->slab_hi, c->has_left, c->has_right, c->ghost_cap,
+            c->send_l, c->send_l2, c->aux_sl, c->send_r, c->send_r2, c->aux_sr, c->xcnt);
+        c->launches += 2;
+        rc = exchange_counts(c);
+        if (rc) return rc;
+        const unsigned out_l = c->h_xcnt[0].leave_l, out_r = c->h_xcnt[0].leave_r;
+        const unsigned in_l = c->has_left ? c->h_xcnt[1].leave_r : 0u, in_r = c->has_right ? c->h_xcnt[2].leave_l : 0u;
+        if (out_l > c->ghost_cap || out_r > c->ghost_cap || in_l + in_r > c->ghost_cap || (unsigned long long)n + in_l + in_r > c->cap)
+            CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "migration buffers too small (out %u/%u in %u/%u)", out_l, out_r, in_l, in_r);
+        if (out_l + out_r + in_l + in_r > 0) {
+            const size_t e = sizeof(Real4), a = sizeof(MigrantAux);
+            Real4* pdst = c->pos[c->cur_pos] + n;
+            Real4* vdst = c->vel[c->cur] + n;
+            NCCL_TRY(c, c->nccl.GroupStart());
+            if (c->has_left) {
+                NCCL_TRY(c, c->nccl.Send(c->send_l, out_l * e, ncclChar, c->rank - 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Send(c->send_l2, out_l * e, ncclChar, c->rank - 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Send(c->aux_sl, out_l * a, ncclChar, c->rank - 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Recv(pdst, in_l * e, ncclChar, c->rank - 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Recv(vdst, in_l * e, ncclChar, c->rank - 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Recv(c->aux_rl, in_l * a, ncclChar, c->rank - 1, c->comm, st));
+            }
+            if (c->has_right) {
+                NCCL_TRY(c, c->nccl.Send(c->send_r, out_r * e, ncclChar, c->rank + 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Send(c->send_r2, out_r * e, ncclChar, c->rank + 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Send(c->aux_sr, out_r * a, ncclChar, c->rank + 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Recv(pdst + in_l, in_r * e, ncclChar, c->rank + 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Recv(vdst + in_l, in_r * e, ncclChar, c->rank + 1, c->comm, st));
+                NCCL_TRY(c, c->nccl.Recv(c->aux_rr, in_r * a, ncclChar, c->rank + 1, c->comm, st));
+            }
+            NCCL_TRY(c, c->nccl.GroupEnd());
+            if (in_l) k_unpack_arrivals<<<div_up(in_l, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(in_l, n, c->aux_rl, c->kappa[c->cur], c->kappa_v[c->cur], c->id[c->cur], c->state[c->cur]);
+            if (in_r) k_unpack_arrivals<<<div_up(in_r, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(in_r, n + in_l, c->aux_rr, c->kappa[c->cur], c->kappa_v[c->cur], c->id[c->cur], c->state[c->cur]);
+        }
+        c->migrated_in += in_l + in_r;
+        c->migrated_out += out_l + out_r;
+        const unsigned n1 = n + in_l + in_r;
+        { ProfScope ps(c, DFSPH_B200_PROF_SORT); rc = cell_sort(c, c->pos[c->cur_pos], n1, c->cell_start, true); }
+        if (rc) return rc;
+        n = n1 - out_l - out_r;   // leavers sit in the dump cell behind the kept particles
+        c->n = n;
+    } else {
+        ProfScope ps(c, DFSPH_B200_PROF_SORT);
+        rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start);
+        if (rc) return rc;
+    }
+    c->ng = c->ng_l = c->ng_r = 0;
     if (n > 0) {
         const int src = c->cur, dst = 1 - c->cur;
         const int psrc = c->cur_pos, pdst = 1 - c->cur_pos;
-        { ProfScope ps(c, DFSPH_B200_PROF_SORT);
+        ProfScope ps(c, DFSPH_B200_PROF_SORT);
         k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
-            c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc); }
+            c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc);
         c->cur = dst; c->cur_pos = pdst;
+        c->launches++;
+    }
+    if (c->multi) {
+        // ---- ghost layer: one cell width of the neighbouring slabs, appended behind the owned particles ---------------
+        k_zero_counts<<<1, 1, 0, st>>>(c->xcnt);
+        const double width = 1.0 / c->grid.inv_cell;
+        if (n > 0) k_select_exports<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->pos[c->cur_pos], c->slab_lo, c->slab_hi, width,
+            c->has_left, c->has_right, c->ghost_cap, c->exp_l, c->exp_r, c->xcnt);
+        c->launches += 2;
+        rc = exchange_counts(c);
+        if (rc) return rc;
+        c->n_exp_l = c->h_xcnt[0].exp_l; c->n_exp_r = c->h_xcnt[0].exp_r;
+        c->ng_l = c->has_left ? c->h_xcnt[1].exp_r : 0u;
+        c->ng_r = c->has_right ? c->h_xcnt[2].exp_l : 0u;
+        c->ng = c->ng_l + c->ng_r;
+        if (c->n_exp_l > c->ghost_cap || c->n_exp_r > c->ghost_cap || c->ng > c->ghost_cap)
+            CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "ghost buffers too small (export %u/%u, ghosts %u, capacity %u)", c->n_exp_l, c->n_exp_r, c->ng, c->ghost_cap);
+        rc = exchange_ghosts(c, c->pos[c->cur_pos]); if (rc) return rc;
+        rc = exchange_ghosts(c, c->vel[c->cur]); if (rc) return rc;
+        k_write_sentinel<<<1, 1, 0, st>>>(c->pos[c->cur_pos], c->vel[c->cur], c->acc, n + c->ng);
+        if (c->ng > 0) CUDA_TRY(c, cudaMemsetAsync(c->acc + n, 0, (size_t)c->ng * sizeof(Real4), st));
+        c->launches++;
+        // ghost cell table (ghosts stay in arrival order; the permutation is left in sorted_idx)
+        rc = cell_sort(c, c->pos[c->cur_pos] + n, c->ng, c->gcell_start);
+        if (rc) return rc;
+        // global particle count = divisor of the average density error
+        const unsigned long long nn = n;
+        CUDA_TRY(c, cudaMemcpyAsync(&c->ctrl->n_global, &nn, sizeof(nn), cudaMemcpyHostToDevice, st));
+        NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->n_global, &c->ctrl->n_global, 1, ncclUint64, ncclSum, c->comm, st));
+    } else if (n == 0) {
+        k_write_sentinel<<<1, 1, 0, st>>>(c->pos[c->cur_pos], c->vel[c->cur], c->acc, 0);
+    }
+    if (n > 0) {
         ProfScope ps(c, DFSPH_B200_PROF_BUILD);
         k_build_neighbors<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
-            c->bpos, c->bcell_start, c->nb, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl);
-        c->launches += 2;
+            c->bpos, c->bcell_start, c->nb, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
+            c->ng, c->gcell_start, c->sorted_idx);
+        c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
     c->tables_valid = true;
@@ -752,6 +923,8 @@ static int run_solver(dfsph_b200_ctx* c)
     const bool div = c->par.enable_divergence_solver != 0;
     FluidArrays f = fluid_arrays(c);
 
+    const bool multi = c->multi;
+    Real4* gpos = c->pos[c->cur_pos];
     { ProfScope ps(c, DFSPH_B200_PROF_INIT);
     if (div) k_init_sweep<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl);
     else k_init_sweep<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl); }
@@ -766,10 +939,18 @@ static int run_solver(dfsph_b200_ctx* c)
         while (true) {
             for (unsigned b = 0; b < batch; ++b) {
                 const int seq = (int)(launched + b);
+                if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }          // kappa of the ghosts (pos.w)
                 { ProfScope ps(c, DFSPH_B200_PROF_ACCEL, seq); k_accel<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl); }
+                if (multi) { int rg = exchange_ghosts(c, c->acc); if (rg) return rg; }        // pressure acceleration of the ghosts
                 if (solve == SOLVE_DIV) { ProfScope ps(c, DFSPH_B200_PROF_JACOBI_DIV, seq); k_jacobi<MODE, SOLVE_DIV><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial); }
                 else { ProfScope ps(c, DFSPH_B200_PROF_JACOBI_PRESS, seq); k_jacobi<MODE, SOLVE_PRESS><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial); }
                 c->launches += 2;
+                if (multi) {
+                    NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->err_sum, &c->ctrl->err_sum, 1, ncclDouble, ncclSum, c->comm, st));
+                    if (solve == SOLVE_DIV) k_solve_control<SOLVE_DIV><<<1, 1, 0, st>>>(c->ctrl, sp, c->sph);
+                    else k_solve_control<SOLVE_PRESS><<<1, 1, 0, st>>>(c->ctrl, sp, c->sph);
+                    c->launches++;
+                }
             }
             launched += batch;
             CUDA_TRY(c, cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -792,11 +973,16 @@ static int run_solver(dfsph_b200_ctx* c)
         // the reference's iteration is a no-op for an empty model: avg stays 0, one iteration is counted
         int rc = solve_loop(SOLVE_DIV, c->par.max_iterations_v, c->pred_iter_v);
         if (rc) return rc;
+        if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
         ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
         k_div_final<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
     } else {
         ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
         k_div_final<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
+    }
+    if (multi) {
+        NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->maxvel_bits, &c->ctrl->maxvel_bits, 1, ncclUint64, ncclMax, c->comm, st));   // CFL maximum
+        int rg = exchange_ghosts(c, c->vel[c->cur]); if (rg) return rg;                                                       // kicked velocities
     }
     k_update_time_step<<<1, 1, 0, st>>>(c->ctrl, sp);
     { ProfScope ps(c, DFSPH_B200_PROF_PRESS_INIT); k_press_init<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl); }
@@ -805,6 +991,7 @@ static int run_solver(dfsph_b200_ctx* c)
         int rc = solve_loop(SOLVE_PRESS, c->par.max_iterations, c->pred_iter);
         if (rc) return rc;
     }
+    if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
     Real4* pos_out = c->pos[1 - c->cur_pos];
     { ProfScope ps(c, DFSPH_B200_PROF_PRESS_FINAL); k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out); }
     k_step_end<<<1, 1, 0, st>>>(c->ctrl);
@@ -915,6 +1102,7 @@ int dfsph_b200_download(dfsph_b200_ctx* c, dfsph_b200_field field, void* dst, si
     if (bytes != (size_t)n * eb) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "size mismatch: field needs %zu bytes, got %zu", (size_t)n * eb, bytes);
     if (n == 0) return DFSPH_B200_OK;
     { int rc = ensure_stage(c, (size_t)n * eb); if (rc) return rc; }
+    if (by_id && c->multi) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "by_id transfers are not available in multi-GPU runs (ids are global): use by_id=0 and FIELD_ID");
     const unsigned* idmap = by_id ? c->id[c->cur] : nullptr;
     const unsigned g = div_up(n, 256);
     switch (field) {
@@ -966,6 +1154,7 @@ int dfsph_b200_step_host(dfsph_b200_ctx* c, void* x_inout, void* v_inout, void* 
 {
     CHECK_CTX(c);
     cudaSetDevice(c->cfg.device);
+    if (c->multi) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "step_host addresses particles by id; in multi-GPU runs use step + download(by_id=0) with FIELD_ID");
     if (!x_inout || !v_inout) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "x/v buffers are NULL");
     const unsigned n = c->n;
     const size_t b3 = (size_t)n * 3 * sizeof(Real);
@@ -1121,6 +1310,44 @@ void* dfsph_b200_alloc_pinned(size_t bytes)
     return p;
 }
 void dfsph_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------
+int dfsph_b200_comm_get_unique_id(void* id128)
+{
+    static NcclApi api;
+    std::string err;
+    if (!id128 || !api.load(err)) { g_create_error = err.empty() ? "null argument" : err; return DFSPH_B200_ERR_COMM; }
+    ncclUniqueId id;
+    if (api.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return DFSPH_B200_ERR_COMM; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128, int rank, int world, double slab_lo, double slab_hi)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!id128 || world < 1 || rank < 0 || rank >= world) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "bad rank/world");
+    if (c->cap != 0) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "dfsph_b200_comm_init must be called before set_fluid");
+    bool given = false;
+    for (int k = 0; k < 3; ++k) if (c->cfg.domain_max[k] > c->cfg.domain_min[k]) given = true;
+    if (!given) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "multi-GPU runs need an explicit cell-grid domain (config.domain_min/max) shared by all ranks");
+    if (!(slab_hi > slab_lo)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "empty slab");
+    if (world == 1) return DFSPH_B200_OK;
+    std::string err;
+    if (!c->nccl.load(err)) CTX_FAIL(c, DFSPH_B200_ERR_COMM, "%s", err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCCL_TRY(c, c->nccl.CommInitRank(&c->comm, world, id, rank));
+    c->multi = true;
+    c->rank = rank; c->world = world;
+    c->has_left = rank > 0; c->has_right = rank < world - 1;
+    c->slab_lo = slab_lo; c->slab_hi = slab_hi;
+    const unsigned one = 1u;
+    CUDA_TRY(c, cudaMemcpy(&c->ctrl->multi, &one, sizeof(one), cudaMemcpyHostToDevice));
+    return DFSPH_B200_OK;
+}
 
 int dfsph_b200_set_profiling(dfsph_b200_ctx* c, int on)
 {

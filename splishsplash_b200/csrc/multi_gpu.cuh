@@ -1,0 +1,131 @@
+// Multi-GPU slab decomposition along x (SURVEY.md row e): one context per GPU / process, ghost particles of one
+// support radius appended behind the owned particles, refreshed over NCCL send/recv; particle migration each step;
+// the density-error sum and the CFL maximum are all-reduced so that every rank takes identical loop decisions.
+// NCCL is resolved at run time with dlopen (the process usually already holds torch's libnccl.so.2).
+#pragma once
+#include "common.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <string>
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+
+    bool load(std::string& err)
+    {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) { err = std::string("libnccl lacks ") + name; return false; }
+        NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        NCCL_SYM(Send, "ncclSend")
+        NCCL_SYM(Recv, "ncclRecv")
+        NCCL_SYM(GroupStart, "ncclGroupStart")
+        NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        NCCL_SYM(AllReduce, "ncclAllReduce")
+        NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+        return true;
+    }
+};
+
+// device-side counters of the exchange, read by the host once per phase
+struct ExchangeCounts {
+    unsigned leave_l, leave_r;     // owned particles that crossed the left / right slab face
+    unsigned exp_l, exp_r;         // owned particles within one cell of the left / right face (ghost exports)
+};
+
+// ---- migration --------------------------------------------------------------------------------------------------
+struct MigrantAux { Real kappa, kappa_v; unsigned id, state; };
+
+// Owned particles outside [lo, hi) are packed for the neighbour rank (atomic compaction).  They are dropped from the
+// owned set by the cell sort, which files them under the dump key `num_keys` (see k_cell_hash_slab).
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_pack_leavers(unsigned n, const Real4* __restrict__ pos, const Real4* __restrict__ vel,
+    const Real* __restrict__ kappa, const Real* __restrict__ kappa_v, const unsigned* __restrict__ id, const unsigned* __restrict__ state,
+    double lo, double hi, int has_left, int has_right, unsigned cap,
+    Real4* __restrict__ pl, Real4* __restrict__ vl, MigrantAux* __restrict__ al,
+    Real4* __restrict__ pr, Real4* __restrict__ vr, MigrantAux* __restrict__ ar, ExchangeCounts* cnt)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Real4 p = pos[i];
+    const double x = (double)p.x;
+    if (has_left && x < lo) {
+        const unsigned k = atomicAdd(&cnt->leave_l, 1u);
+        if (k < cap) { pl[k] = p; vl[k] = vel[i]; al[k] = MigrantAux{kappa[i], kappa_v[i], id[i], state[i]}; }
+    } else if (has_right && x >= hi) {
+        const unsigned k = atomicAdd(&cnt->leave_r, 1u);
+        if (k < cap) { pr[k] = p; vr[k] = vel[i]; ar[k] = MigrantAux{kappa[i], kappa_v[i], id[i], state[i]}; }
+    }
+}
+
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_unpack_arrivals(unsigned count, unsigned base, const MigrantAux* __restrict__ aux,
+    Real* __restrict__ kappa, Real* __restrict__ kappa_v, unsigned* __restrict__ id, unsigned* __restrict__ state)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const MigrantAux a = aux[k];
+    kappa[base + k] = a.kappa; kappa_v[base + k] = a.kappa_v; id[base + k] = a.id; state[base + k] = a.state;
+}
+
+// cell hash with the slab filter: leavers get the dump key (sorted behind every real cell, then cut off)
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash_slab(const Real4* __restrict__ pos, unsigned n, GridDesc g, double lo, double hi,
+    int has_left, int has_right, unsigned* __restrict__ cell_count, unsigned* __restrict__ key_out, unsigned* __restrict__ rank_out,
+    unsigned* __restrict__ fine_out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Real4 p = pos[i];
+    unsigned sx, sy, sz;
+    const int cx = cell_coord_fine(p.x, g.ox, g.inv_cell, g.nx, sx);
+    const int cy = cell_coord_fine(p.y, g.oy, g.inv_cell, g.ny, sy);
+    const int cz = cell_coord_fine(p.z, g.oz, g.inv_cell, g.nz, sz);
+    unsigned key = cell_key(cx, cy, cz, g);
+    const double x = (double)p.x;
+    if ((has_left && x < lo) || (has_right && x >= hi)) key = g.num_keys;
+    key_out[i] = key;
+    fine_out[i] = spread3(sx) | (spread3(sy) << 1) | (spread3(sz) << 2);
+    rank_out[i] = atomicAdd(cell_count + key, 1u);
+}
+
+// ---- ghost exports -------------------------------------------------------------------------------------------------
+// Owned (sorted) particles within `width` of a slab face are exported to that neighbour.
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_select_exports(unsigned n, const Real4* __restrict__ pos, double lo, double hi, double width,
+    int has_left, int has_right, unsigned cap, unsigned* __restrict__ exp_l, unsigned* __restrict__ exp_r, ExchangeCounts* cnt)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = (double)pos[i].x;
+    if (has_left && x < lo + width) { const unsigned k = atomicAdd(&cnt->exp_l, 1u); if (k < cap) exp_l[k] = i; }
+    if (has_right && x >= hi - width) { const unsigned k = atomicAdd(&cnt->exp_r, 1u); if (k < cap) exp_r[k] = i; }
+}
+
+// gather one Real4 field of the export lists into the two send buffers
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_pack_exports(const Real4* __restrict__ src, const unsigned* __restrict__ exp_l, unsigned nl,
+    const unsigned* __restrict__ exp_r, unsigned nr, Real4* __restrict__ out_l, Real4* __restrict__ out_r)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nl) st_real4(out_l + k, ld_plain(src + exp_l[k]));
+    else if (k < nl + nr) st_real4(out_r + (k - nl), ld_plain(src + exp_r[k - nl]));
+}
+
+__global__ void k_write_sentinel(Real4* pos, Real4* vel, Real4* acc, unsigned at)
+{
+    st_real4(pos + at, make_real4((Real)1.0e15, (Real)1.0e15, (Real)1.0e15, (Real)0.0));
+    st_real4(vel + at, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+    st_real4(acc + at, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+}
+
+__global__ void k_zero_counts(ExchangeCounts* c) { c->leave_l = c->leave_r = c->exp_l = c->exp_r = 0u; }

@@ -209,15 +209,17 @@ __device__ __forceinline__ bool neighbor_predicate(Real4 a, Real4 b, Real R2)
 
 // One thread per particle of the searching set; walks the 27 cells around its cell in the `other` set's cell table.
 // SELF: searching set == found set (skip j == i).
-template <bool SELF>
+// PERM: the found set is not stored in cell order; `perm` maps cell-table slots to its particles (ghost set) and the
+// table receives `base + particle`.  `cnt` continues an existing list (ghosts are appended to the fluid list).
+template <bool SELF, bool PERM>
 __device__ __forceinline__ unsigned search_cells(const Real4 xi, unsigned i, const GridDesc& g, Real R2,
     const Real4* __restrict__ other_pos, const unsigned* __restrict__ other_cell_start,
-    unsigned* __restrict__ tab, unsigned K, unsigned tile, unsigned lane)
+    unsigned* __restrict__ tab, unsigned K, unsigned tile, unsigned lane,
+    unsigned cnt = 0, const unsigned* __restrict__ perm = nullptr, unsigned base = 0)
 {
     const int cx = cell_coord(xi.x, g.ox, g.inv_cell, g.nx);
     const int cy = cell_coord(xi.y, g.oy, g.inv_cell, g.ny);
     const int cz = cell_coord(xi.z, g.oz, g.inv_cell, g.nz);
-    unsigned cnt = 0;
     unsigned* my = tab + (size_t)tile * K * DFSPH_TILE + lane;
     // z outermost / x innermost = ascending Morton order inside a block: lists come out (nearly) sorted by address
     for (int dz = -1; dz <= 1; ++dz) {
@@ -231,10 +233,11 @@ __device__ __forceinline__ unsigned search_cells(const Real4 xi, unsigned i, con
                 if (x < 0 || x >= g.nx) continue;
                 const unsigned key = cell_key(x, y, z, g);
                 const unsigned s = __ldg(other_cell_start + key), e = __ldg(other_cell_start + key + 1);
-                for (unsigned j = s; j < e; ++j) {
+                for (unsigned k = s; k < e; ++k) {
+                    const unsigned j = PERM ? __ldg(perm + k) : k;
                     const Real4 xj = ld_gather(other_pos + j);
                     if (neighbor_predicate(xi, xj, R2) && !(SELF && j == i)) {
-                        if (cnt < K) my[(size_t)cnt * DFSPH_TILE] = j;
+                        if (cnt < K) my[(size_t)cnt * DFSPH_TILE] = base + j;
                         ++cnt;
                     }
                 }
@@ -248,15 +251,18 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_build_neighbors(unsigned n, Gri
     const Real4* __restrict__ pos, const unsigned* __restrict__ cell_start,
     const Real4* __restrict__ bpos, const unsigned* __restrict__ bcell_start, unsigned nb,
     unsigned* __restrict__ tab_f, unsigned Kf, unsigned* __restrict__ tab_b, unsigned Kb,
-    unsigned* __restrict__ cnt_f, unsigned* __restrict__ cnt_b, unsigned* __restrict__ tcnt_f, unsigned* __restrict__ tcnt_b, Ctrl* ctrl)
+    unsigned* __restrict__ cnt_f, unsigned* __restrict__ cnt_b, unsigned* __restrict__ tcnt_f, unsigned* __restrict__ tcnt_b, Ctrl* ctrl,
+    unsigned ng, const unsigned* __restrict__ gcell_start, const unsigned* __restrict__ gperm)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned tile = i >> 5, lane = i & 31u;
     const Real4 xi = ld_gather(pos + i);
-    const unsigned cf = search_cells<true>(xi, i, g, R2, pos, cell_start, tab_f, Kf, tile, lane);
+    unsigned cf = search_cells<true, false>(xi, i, g, R2, pos, cell_start, tab_f, Kf, tile, lane);
+    // multi-GPU: ghost particles of the neighbouring slabs live behind the owned ones at pos[n .. n+ng)
+    if (ng > 0) cf = search_cells<false, true>(xi, i, g, R2, pos + n, gcell_start, tab_f, Kf, tile, lane, cf, gperm, n);
     unsigned cb = 0;
-    if (nb > 0) cb = search_cells<false>(xi, i, g, R2, bpos, bcell_start, tab_b, Kb, tile, lane);
+    if (nb > 0) cb = search_cells<false, false>(xi, i, g, R2, bpos, bcell_start, tab_b, Kb, tile, lane);
     const unsigned sf = cf < Kf ? cf : Kf, sb = cb < Kb ? cb : Kb;
     cnt_f[i] = sf;
     cnt_b[i] = sb;
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_build_neighbors(unsigned n, Gri
     const unsigned mf = (__reduce_max_sync(mask, sf) + (DFSPH_PAD - 1u)) & ~(DFSPH_PAD - 1u);
     const unsigned mb = (__reduce_max_sync(mask, sb) + (DFSPH_PAD - 1u)) & ~(DFSPH_PAD - 1u);
     unsigned* pf = tab_f + (size_t)tile * Kf * DFSPH_TILE + lane;
-    for (unsigned k = sf; k < mf; ++k) pf[(size_t)k * DFSPH_TILE] = n;
+    for (unsigned k = sf; k < mf; ++k) pf[(size_t)k * DFSPH_TILE] = n + ng;   // sentinel sits behind the ghosts
     unsigned* pb = tab_b + (size_t)tile * Kb * DFSPH_TILE + lane;
     for (unsigned k = sb; k < mb; ++k) pb[(size_t)k * DFSPH_TILE] = nb;
     if (lane == (unsigned)(__ffs(mask) - 1)) {

@@ -295,6 +295,25 @@ struct JacobiF {
     }
 };
 
+// loop control (TimeStepDFSPH.cpp:324-341 / 477-495) on the reduced density error; one thread
+template <int SOLVE>
+__device__ __forceinline__ void solve_control(Ctrl* ctrl, const SolverParams& sp, const SphConst& c, unsigned long long n)
+{
+    const Real density_error = (Real)ctrl->err_sum;
+    const Real avg = n > 0ull ? density_error / (Real)n : (Real)0.0;   // empty model: iteration is a no-op (:550-551)
+    Real eta;
+    unsigned min_it, max_it;
+    if (SOLVE == SOLVE_PRESS) { eta = sp.max_error * (Real)0.01 * c.density0; min_it = sp.min_iter; max_it = sp.max_iter; }
+    else { eta = ((Real)1.0 / ctrl->h) * sp.max_error_v * (Real)0.01 * c.density0; min_it = 1u; max_it = sp.max_iter_v; }
+    const bool chk = avg <= eta;
+    const unsigned it = ctrl->iter + 1u;
+    ctrl->iter = it;
+    if (SOLVE == SOLVE_PRESS) { ctrl->avg_err = (double)avg; ctrl->iterations = it; }
+    else { ctrl->avg_err_v = (double)avg; ctrl->iterations_v = it; }
+    const bool cont = (!chk || (it < min_it)) && (it < max_it);
+    ctrl->done = cont ? 0 : 1;
+}
+
 template <int MODE, int SOLVE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial)
 {
@@ -334,22 +353,18 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst 
         for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += partial[b];
         t = block_sum_double(t);
         if (threadIdx.x == 0) {
-            // loop control (TimeStepDFSPH.cpp:324-341 / 477-495)
-            const Real density_error = (Real)t;
-            const Real avg = f.n > 0u ? density_error / (Real)f.n : (Real)0.0;   // empty model: iteration is a no-op (:550-551)
-            Real eta;
-            unsigned min_it, max_it;
-            if (SOLVE == SOLVE_PRESS) { eta = sp.max_error * (Real)0.01 * c.density0; min_it = sp.min_iter; max_it = sp.max_iter; }
-            else { eta = ((Real)1.0 / ctrl->h) * sp.max_error_v * (Real)0.01 * c.density0; min_it = 1u; max_it = sp.max_iter_v; }
-            const bool chk = avg <= eta;
-            const unsigned it = ctrl->iter + 1u;
-            ctrl->iter = it;
-            if (SOLVE == SOLVE_PRESS) { ctrl->avg_err = (double)avg; ctrl->iterations = it; }
-            else { ctrl->avg_err_v = (double)avg; ctrl->iterations_v = it; }
-            const bool cont = (!chk || (it < min_it)) && (it < max_it);
-            ctrl->done = cont ? 0 : 1;
+            ctrl->err_sum = t;
+            if (!ctrl->multi) solve_control<SOLVE>(ctrl, sp, c, (unsigned long long)f.n);
         }
     }
+}
+
+// multi-GPU: runs after ncclAllReduce(sum) of ctrl->err_sum; every rank takes the identical decision
+template <int SOLVE>
+__global__ void k_solve_control(Ctrl* ctrl, SolverParams sp, SphConst c)
+{
+    if (ctrl->done) return;
+    solve_control<SOLVE>(ctrl, sp, c, ctrl->n_global);
 }
 
 // Start of a solve: reset the loop state.  For n == 0 the reference's iteration returns immediately with avg = 0.

@@ -43,7 +43,7 @@ class TimeStepDFSPH_B200:
         cfg.max_fluid_neighbors = max_fluid_neighbors
         cfg.max_boundary_neighbors = max_boundary_neighbors
         cfg.max_fluid_particles = max_fluid_particles
-        if domain is not None:
+        if domain is not None:   # explicit cell-grid extent (mandatory and identical on all ranks in multi-GPU runs)
             for k in range(3):
                 cfg.domain_min[k] = float(domain[0][k])
                 cfg.domain_max[k] = float(domain[1][k])

@@ -1,0 +1,72 @@
+"""Multi-GPU parity check (run with torchrun --nproc-per-node 2): a dam-break block split into x-slabs must reproduce
+the single-GPU run of the same global scene: per-field agreement by particle id and identical iteration counts."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from splishsplash_b200 import scenes, parallel  # noqa: E402
+from splishsplash_b200.solver import build_b200_scene  # noqa: E402
+from tests.parity import scaled_err, dtype_of  # noqa: E402
+
+
+def main():
+    prec = sys.argv[1] if len(sys.argv) > 1 else "f64"
+    name = sys.argv[2] if len(sys.argv) > 2 else "small"
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sc = scenes.dam_break(name, dtype=dtype_of(prec))
+    # give the block an initial velocity towards +x so that particles migrate across the slab faces
+    v = np.zeros_like(sc["fluid_x"]); v[:, 0] = 0.8
+    sc["fluid_v"] = v
+    mine = parallel.select_slab(sc, rank, world)
+    # boundary volumes must come from the global boundary (a per-rank subset would change V near the cut)
+    single = build_b200_scene(sc, prec, device=local) if True else None
+    bV = single.boundary_volume()
+    ts = parallel.build_b200_slab(mine, prec, rank, world, device=local, boundary_V=bV[mine["boundary_keep"]])
+    fields = ["position", "velocity", "density", "factor", "p / rho^2", "p_v / rho^2", "advected density"]
+    ok = True
+    iters_m, iters_s = [], []
+    for s in range(steps):
+        st = ts.step(1)
+        ss = single.step(1)
+        iters_m.append((st.iterations_v, st.iterations)); iters_s.append((ss.iterations_v, ss.iterations))
+    ids = ts.field("id", by_id=False)
+    local_fields = {f: ts.field(f, by_id=False) for f in fields}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ids, local_fields, ts.num_particles))
+    if rank == 0:
+        n = len(sc["fluid_x"])
+        counts = [g[2] for g in gathered]
+        all_ids = np.concatenate([g[0] for g in gathered])
+        assert len(all_ids) == n and len(np.unique(all_ids)) == n, ("particles lost or duplicated", counts, n)
+        worst = {}
+        for f in fields:
+            ref = single.field(f)
+            got = np.empty_like(ref)
+            for g in gathered:
+                got[g[0]] = g[1][f]
+            worst[f] = scaled_err(got, ref)
+        tol = (1e-8 if prec == "f64" else 2e-3)   # free-running for `steps` steps: rounding differences accumulate
+        same_iters = iters_m == iters_s
+        ok = same_iters and all(e <= tol for e in worst.values())
+        print(f"[{prec} {name} world={world}] owned per rank {counts} steps={steps} iters equal={same_iters} "
+              f"worst={max(worst.items(), key=lambda kv: kv[1])} ok={ok}")
+        print("   ", {k: f"{e:.2e}" for k, e in worst.items()})
+        if not same_iters:
+            print("    multi:", iters_m, "\n    single:", iters_s)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    ts.close(); single.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
