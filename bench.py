@@ -189,10 +189,17 @@ def main():
     from splishsplash_b200.solver import build_b200_scene
 
     dt = np.float32 if args.precision == "f32" else np.float64
-    # weak scaling: every rank owns one block of the named size
-    sc = scenes.dam_break(args.particles, dtype=dt)
-    ts = build_b200_scene(sc, args.precision, device=local_rank, **solver_params())
+    if world == 1:
+        sc = scenes.dam_break(args.particles, dtype=dt)
+        ts = build_b200_scene(sc, args.precision, device=local_rank, **solver_params())
+    else:
+        # weak scaling: `world` blocks of the named size side by side in one tank, one x-slab per GPU, ghost exchange and
+        # migration over NCCL inside the library (splishsplash_b200/csrc/multi_gpu.cuh)
+        from splishsplash_b200 import parallel
+        sc = scenes.dam_break_weak(rank, world, args.particles, dtype=dt)
+        ts = parallel.build_b200_slab(sc, args.precision, rank, world, device=local_rank, **solver_params())
     n = ts.num_particles
+    n_global = n if world == 1 else sc["global_particles"]
 
     def barrier():
         ts.synchronize()
@@ -222,19 +229,36 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
-    # ---- end-to-end through host buffers
+    # ---- end-to-end through host buffers (pinned): H2D of x, v and D2H of x, v, density inside the timed region
+    n = ts.num_particles          # (migration may have changed the local count)
     x = ts.pinned((n, 3))
     v = ts.pinned((n, 3))
     rho = ts.pinned((n,))
-    x[:] = ts.field("position")
-    v[:] = ts.field("velocity")
+    if world == 1:
+        x[:] = ts.field("position")
+        v[:] = ts.field("velocity")
+        e2e_step = lambda: ts.step_host(x, v, rho)
+    else:
+        # multi-GPU: the host buffers are in device order (ids are global); upload, step, download
+        x[:] = ts.field("position", by_id=False)
+        v[:] = ts.field("velocity", by_id=False)
+
+        def e2e_step():
+            m = ts.num_particles
+            ts.set_field("position", x[:m], by_id=False)
+            ts.set_field("velocity", v[:m], by_id=False)
+            ts.step(1)
+            m2 = min(ts.num_particles, n)
+            x[:m2] = ts.field("position", by_id=False)[:m2]
+            v[:m2] = ts.field("velocity", by_id=False)[:m2]
+            rho[:m2] = ts.field("density", by_id=False)[:m2]
     for _ in range(2):
-        ts.step_host(x, v, rho)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     ts.timer_start()
     for _ in range(args.e2e_steps):
-        ts.step_host(x, v, rho)
+        e2e_step()
     ms_e2e = ts.timer_stop()
     wall_e2e = (time.perf_counter() - t0) * 1000.0
     ms_e2e = max(ms_e2e, wall_e2e)   # host-side copies are synchronous: take the larger of device and wall time
@@ -257,11 +281,12 @@ def main():
         npr = float(np.mean([i[1] for i in iters]))
         step_bytes = ((101 + 17 * (nv + npr)) * R + 32) * n
         line = {
-            "metric": METRIC, "value": world * n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": dict(cfg, parallelism=("single GPU" if world == 1 else f"{world} independent blocks (no halo exchange in this round)")),
-            "e2e": {"value": world * n * args.e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "config": dict(cfg, parallelism=("single GPU" if world == 1 else
+                                             f"{world} x-slabs, one per GPU, NCCL ghost exchange (x,v per step; kappa, a per iteration) + migration")),
+            "e2e": {"value": n_global * args.e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -81,13 +81,38 @@ def fluid_block(box_min, box_max, radius, dtype=np.float32, dense_mode=0):
     return x.reshape(-1, 3)
 
 
-def box_boundary(box_min, box_max, radius, dtype=np.float32, spacing_factor=1.5):
-    """One layer of boundary particles on the six faces of an axis-aligned box, no duplicates on edges."""
+def box_boundary(box_min, box_max, radius, dtype=np.float32, spacing_factor=1.5, x_range=None):
+    """One layer of boundary particles on the six faces of an axis-aligned box, no duplicates on edges.
+    x_range = (a, b): only the particles with a <= x < b are generated (per-rank portion of a long tank)."""
     bmin = np.asarray(box_min, dtype=np.float64)
     bmax = np.asarray(box_max, dtype=np.float64)
     s = spacing_factor * float(radius)
     n = [max(int(round((bmax[k] - bmin[k]) / s)), 1) for k in range(3)]
     ax = [np.linspace(bmin[k], bmax[k], n[k] + 1) for k in range(3)]
+    if x_range is not None:
+        a, b = x_range
+        xs = ax[0]
+        first, last = xs[0], xs[-1]
+        inner = xs[1:-1]
+        inner = inner[(inner >= a) & (inner < b)]
+        ends = np.array([v for v in (first, last) if a <= v < b])
+        parts = []
+
+        def grid_(p, q, r):
+            g = np.empty((len(p), len(q), len(r), 3), dtype=np.float64)
+            g[..., 0] = p[:, None, None]
+            g[..., 1] = q[None, :, None]
+            g[..., 2] = r[None, None, :]
+            return g.reshape(-1, 3)
+
+        if len(ends):
+            parts.append(grid_(ends, ax[1], ax[2]))
+        if len(inner):
+            parts.append(grid_(inner, ax[1][[0, -1]], ax[2]))
+            parts.append(grid_(inner, ax[1][1:-1], ax[2][[0, -1]]))
+        if not parts:
+            return np.zeros((0, 3), dtype=dtype)
+        return np.ascontiguousarray(np.concatenate(parts, axis=0).astype(dtype))
 
     def grid(a, b, c):
         g = np.empty((len(a), len(b), len(c), 3), dtype=np.float64)
@@ -122,6 +147,43 @@ def dam_break(counts="tiny", radius=0.025, dtype=np.float32, tank_x_factor=3.0, 
     bnd = box_boundary(tmin, tmax, radius, dtype, spacing_factor)
     return {"fluid_x": fluid, "boundary_x": bnd, "radius": float(radius), "counts": tuple(counts),
             "tank_min": tmin, "tank_max": tmax}
+
+
+def dam_break_weak(rank, world, counts="10M", radius=0.025, dtype=np.float32, tank_x_factor=3.0, tank_y_factor=1.5,
+                   spacing_factor=1.5, halo_cells=2.0):
+    """Weak-scaling scene: `world` blocks of the named size side by side along x in one long tank; rank
+    r generates ONLY its own block (global particle ids), its slab [lo, hi) and the boundary particles within
+    `halo_cells` cells of the slab.  The global scene is never materialised.  Returns the per-rank dict that
+    splishsplash_b200.parallel.build_b200_slab expects."""
+    if isinstance(counts, str):
+        counts = NAMED_BLOCKS[counts]
+    nx, ny, nz = counts
+    dt = np.dtype(dtype).type
+    d = 2.0 * radius
+    gx = nx * world
+    block = np.array([(gx + 1) * d, (ny + 1) * d, (nz + 1) * d])
+    tmin = np.zeros(3)
+    tmax = np.array([tank_x_factor * block[0], tank_y_factor * block[1], block[2]])
+    # the same position arithmetic as fluid_lattice for the global lattice (index * diam + start, in Real)
+    diam = dt(2.0) * dt(radius)
+    ix = np.arange(rank * nx, (rank + 1) * nx)
+    axx = (ix.astype(dtype) * diam + dt(d)).astype(dtype)
+    axy = (np.arange(ny, dtype=dtype) * diam + dt(d)).astype(dtype)
+    axz = (np.arange(nz, dtype=dtype) * diam + dt(d)).astype(dtype)
+    x = np.empty((nx, ny, nz, 3), dtype=dtype)
+    x[..., 0] = axx[:, None, None]
+    x[..., 1] = axy[None, :, None]
+    x[..., 2] = axz[None, None, :]
+    ids = ((ix[:, None, None].astype(np.int64) * ny + np.arange(ny)[None, :, None]) * nz + np.arange(nz)[None, None, :])
+    # slab faces half-way between lattice planes
+    face = lambda k: d + (k * nx - 0.5) * d
+    lo = -1.0e300 if rank == 0 else face(rank)
+    hi = 1.0e300 if rank == world - 1 else face(rank + 1)
+    cell = 4.0 * radius * (1.0 + 1.0e-5)
+    bnd = box_boundary(tmin, tmax, radius, dtype, spacing_factor, x_range=(lo - halo_cells * cell, hi + halo_cells * cell))
+    return {"fluid_x": x.reshape(-1, 3), "fluid_ids": ids.reshape(-1).astype(np.uint32), "boundary_x": bnd,
+            "radius": float(radius), "counts": tuple(counts), "slab": (lo, hi), "domain": (tmin - cell, tmax + cell),
+            "tank_min": tmin, "tank_max": tmax, "global_particles": int(gx) * ny * nz}
 
 
 def rw_state_scene(dtype=np.float32):

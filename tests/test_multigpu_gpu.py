@@ -1,0 +1,27 @@
+"""GPU test of the multi-GPU path: needs >= 2 CUDA devices (skipped otherwise).  Launches tools/multigpu_check.py with
+torchrun: a dam-break block split into two x-slabs, moving towards +x so that particles migrate, must reproduce the
+single-GPU run of the same scene (identical iteration counts, fields by particle id)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from tests.parity import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_two_slabs_reproduce_single_gpu(prec):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "multigpu_check.py"), prec, "small", "25"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
