@@ -23,9 +23,11 @@ __host__ __device__ __forceinline__ Real4 make_real4(Real x, Real y, Real z, Rea
 __device__ __forceinline__ Real4 ld_gather(const Real4* p)
 {
 #if DFSPH_REAL_IS_DOUBLE
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    return make_real4(a.x, a.y, b.x, b.y);
+    // one 256-bit load (LDG.E.ENL2.256 on sm_100a) instead of two 128-bit ones: a scattered gather costs L1 wavefronts
+    // per request, not per byte (profiles/r1_gather_microbench.md: 23 vs 31 cycles for a 32 B record)
+    Real4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
 #else
     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
     return make_real4(a.x, a.y, a.z, a.w);
@@ -34,9 +36,9 @@ __device__ __forceinline__ Real4 ld_gather(const Real4* p)
 __device__ __forceinline__ Real4 ld_plain(const Real4* p)
 {
 #if DFSPH_REAL_IS_DOUBLE
-    const double2 a = *(reinterpret_cast<const double2*>(p));
-    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
-    return make_real4(a.x, a.y, b.x, b.y);
+    Real4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p) : "memory");
+    return r;
 #else
     const float4 a = *reinterpret_cast<const float4*>(p);
     return make_real4(a.x, a.y, a.z, a.w);
@@ -119,8 +121,8 @@ struct SphConst {
     Real V;            // fluid particle volume (FluidModel::m_V)
     Real density0;
     Real lut_inv_step; // PrecomputedKernel::m_invStepSize
-    const Real* lutW;      // [10000]
-    const Real* lutGradW;  // [10001]
+    const Real* lutW;      // [9999]  pre-averaged: 0.5*(m_W[i] + m_W[i+1]), the exact value the reference computes per call
+    const Real* lutGradW;  // [9999]  pre-averaged: 0.5*(m_gradW[i] + m_gradW[i+1])
     int mode;          // KernelMode used by the solver sums
 };
 

@@ -210,10 +210,17 @@ static int setup_constants(dfsph_b200_ctx* c)
         else G[i] = 0.0;
     }
     G[LUT_RESOLUTION] = 0.0;
+    // The reference evaluates 0.5*(m_W[pos] + m_W[pos+1]) per call (SPHKernels.h:657,682) with pos <= resolution-2.
+    // The same expression is evaluated here once per table slot, so the device needs one load instead of two.
+    std::vector<Real> Wavg(LUT_RESOLUTION, (Real)0.0), Gavg(LUT_RESOLUTION, (Real)0.0);   // slot 9999 = 0: outside the support
+    for (unsigned i = 0; i + 1 < LUT_RESOLUTION; i++) {
+        Wavg[i] = static_cast<Real>(0.5) * (W[i] + W[i + 1]);
+        Gavg[i] = static_cast<Real>(0.5) * (G[i] + G[i + 1]);
+    }
     if (dev_alloc(c, &c->lutW, LUT_RESOLUTION)) return DFSPH_B200_ERR_CUDA;
-    if (dev_alloc(c, &c->lutGradW, LUT_RESOLUTION + 1)) return DFSPH_B200_ERR_CUDA;
-    CUDA_TRY(c, cudaMemcpy(c->lutW, W.data(), W.size() * sizeof(Real), cudaMemcpyHostToDevice));
-    CUDA_TRY(c, cudaMemcpy(c->lutGradW, G.data(), G.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    if (dev_alloc(c, &c->lutGradW, LUT_RESOLUTION)) return DFSPH_B200_ERR_CUDA;
+    CUDA_TRY(c, cudaMemcpy(c->lutW, Wavg.data(), Wavg.size() * sizeof(Real), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->lutGradW, Gavg.data(), Gavg.size() * sizeof(Real), cudaMemcpyHostToDevice));
     s.lutW = c->lutW;
     s.lutGradW = c->lutGradW;
 

@@ -63,6 +63,10 @@ __device__ __forceinline__ void neighbor_sweep(const unsigned* __restrict__ t, u
 #pragma unroll
             for (int u = 0; u < U; ++u) jn[u] = __ldg(t + (size_t)(k + U + u) * DFSPH_TILE);
         }
+        // pair geometry + kernel evaluation for the whole batch first (in lookup-table mode this issues the table
+        // reads of all U pairs before any of them is consumed), then the accumulation
+#pragma unroll
+        for (int u = 0; u < U; ++u) f.prep(d[u]);
 #pragma unroll
         for (int u = 0; u < U; ++u) f.apply(d[u]);
     }
@@ -111,19 +115,21 @@ __device__ __forceinline__ bool last_block(Ctrl* ctrl)
 
 template <int MODE>
 struct InitFluidF {
-    struct Data { Real4 x, v; };
+    struct Data { Real4 x, v; Real rx, ry, rz, g, W; };
     const Real4* pos; const Real4* vel; const SphConst& c;
     Real4 xi, vi;
     Real dens, gx, gy, gz, sum_grad2, dadv;
     __device__ __forceinline__ InitFluidF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_)
         : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), dens(0), gx(0), gy(0), gz(0), sum_grad2(0), dadv(0) {}
     __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.v = ld_gather(vel + j); return d; }
+    __device__ __forceinline__ void prep(Data& d) const
+    {
+        d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+        sph_W_gradW<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz, d.W, d.g);
+    }
     __device__ __forceinline__ void apply(const Data& d)
     {
-        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        Real W, g;
-        sph_W_gradW<MODE>(c, r2, W, g);
+        const Real rx = d.rx, ry = d.ry, rz = d.rz, W = d.W, g = d.g;
         const Real V = c.V;
         dens += V * W;
 #if DFSPH_REAL_IS_DOUBLE
@@ -145,19 +151,21 @@ struct InitFluidF {
 
 template <int MODE>
 struct InitBoundaryF {
-    struct Data { Real4 x; };
+    struct Data { Real4 x; Real rx, ry, rz, g, W; };
     const Real4* bpos; const SphConst& c;
     Real4 xi, vi;
     Real dens, bx, by, bz, dadv;
     __device__ __forceinline__ InitBoundaryF(const Real4* bpos_, const SphConst& c_, Real4 xi_, Real4 vi_)
         : bpos(bpos_), c(c_), xi(xi_), vi(vi_), dens(0), bx(0), by(0), bz(0), dadv(0) {}
     __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(bpos + j); return d; }
+    __device__ __forceinline__ void prep(Data& d) const
+    {
+        d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+        sph_W_gradW<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz, d.W, d.g);
+    }
     __device__ __forceinline__ void apply(const Data& d)   // d.x.w = V_b (0 for the sentinel)
     {
-        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        Real W, g;
-        sph_W_gradW<MODE>(c, r2, W, g);
+        const Real rx = d.rx, ry = d.ry, rz = d.rz, W = d.W, g = d.g;
         dens += d.x.w * W;
         const Real gv = d.x.w * g;
         const Real px = gv * rx, py = gv * ry, pz = gv * rz;
@@ -218,17 +226,20 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphCo
 // ---- pressure acceleration of particle i from the kappa values in pos.w -------------------------------------------
 template <int MODE>
 struct AccelF {
-    struct Data { Real4 x; };
+    struct Data { Real4 x; Real rx, ry, rz, g; };
     const Real4* pos; const SphConst& c;
     Real4 xi;
     Real ax, ay, az;
     __device__ __forceinline__ AccelF(const FluidArrays& f, const SphConst& c_, Real4 xi_) : pos(f.pos), c(c_), xi(xi_), ax(0), ay(0), az(0) {}
     __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(pos + j); return d; }
+    __device__ __forceinline__ void prep(Data& d) const
+    {
+        d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+        d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+    }
     __device__ __forceinline__ void apply(const Data& d)
     {
-        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        const Real g = sph_gradW_scale<MODE>(c, r2);
+        const Real rx = d.rx, ry = d.ry, rz = d.rz, g = d.g;
         const Real pSum = xi.w + d.x.w;   // density0 ratio is 1 (single phase)
 #if DFSPH_REAL_IS_DOUBLE
         if (real_abs(pSum) > DFSPH_EPS) {   // scalar variant skips tiny sums (TimeStepDFSPH.cpp:1323-1327)
@@ -275,17 +286,20 @@ enum { SOLVE_DIV = 0, SOLVE_PRESS = 1 };
 
 template <int MODE>
 struct JacobiF {
-    struct Data { Real4 x, a; };
+    struct Data { Real4 x, a; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* acc; const SphConst& c;
     Real4 xi, ai;
     Real sum;
     __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), xi(xi_), ai(ai_), sum(0) {}
     __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.a = ld_gather(acc + j); return d; }
+    __device__ __forceinline__ void prep(Data& d) const
+    {
+        d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+        d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+    }
     __device__ __forceinline__ void apply(const Data& d)
     {
-        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        const Real g = sph_gradW_scale<MODE>(c, r2);
+        const Real rx = d.rx, ry = d.ry, rz = d.rz, g = d.g;
 #if DFSPH_REAL_IS_DOUBLE
         sum += (ai.x - d.a.x) * (g * rx) + (ai.y - d.a.y) * (g * ry) + (ai.z - d.a.z) * (g * rz);
 #else
@@ -455,17 +469,20 @@ __global__ void k_update_time_step(Ctrl* ctrl, SolverParams sp)
 // ---- pressure solve init -------------------------------------------------------------------------------------------
 template <int MODE>
 struct VelDivF {
-    struct Data { Real4 x, v; };
+    struct Data { Real4 x, v; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* vel; const SphConst& c;
     Real4 xi, vi;
     Real delta;
     __device__ __forceinline__ VelDivF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_) : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), delta(0) {}
     __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.v = ld_gather(vel + j); return d; }
+    __device__ __forceinline__ void prep(Data& d) const
+    {
+        d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+        d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+    }
     __device__ __forceinline__ void apply(const Data& d)
     {
-        const Real rx = xi.x - d.x.x, ry = xi.y - d.x.y, rz = xi.z - d.x.z;
-        const Real r2 = rx * rx + ry * ry + rz * rz;
-        const Real g = sph_gradW_scale<MODE>(c, r2);
+        const Real rx = d.rx, ry = d.ry, rz = d.rz, g = d.g;
 #if DFSPH_REAL_IS_DOUBLE
         delta += (vi.x - d.v.x) * (g * rx) + (vi.y - d.v.y) * (g * ry) + (vi.z - d.v.z) * (g * rz);
 #else
