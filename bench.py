@@ -215,10 +215,13 @@ def main():
     ts.timer_start()
     launches = 0
     iters = []
+    ms_search = ms_solver = 0.0
     for _ in range(args.steps):
         st = ts.step(1)
         launches += st.gpu_launches
         iters.append((st.iterations_v, st.iterations))
+        ms_search += st.ms_search
+        ms_solver += st.ms_solver
     ms = ts.timer_stop()
     clocks = sampler.stop()
     prof = ts.profile()
@@ -299,6 +302,7 @@ def main():
             "kernel_ms_per_step": {k: p[0] / args.steps for k, p in prof.items()},
             "kernel_launches": {k: p[1] for k, p in prof.items()},
             "mean_iterations": {"divergence": nv, "pressure": npr},
+            "ms_search_per_step": ms_search / args.steps, "ms_solver_per_step": ms_solver / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -173,16 +173,16 @@ int dfsph_b200_eval_kernel(dfsph_b200_ctx* ctx, int kernel, uint64_t n, const vo
 
 /* ---- multi-GPU slab decomposition along x: one context per GPU / process (DESIGN.md "Multi-GPU") -------------------
  * The reference has no distributed path at all; these entry points are new.  Rank 0 obtains an id with
- * dfsph_b200_comm_get_unique_id and hands the 128 bytes to every rank (the host layer uses torch.distributed for
+ * dfsph_b200_comm_get_unique_id and hands the 256 bytes to every rank (the host layer uses torch.distributed for
  * that); every rank then calls dfsph_b200_comm_init BEFORE dfsph_b200_set_fluid with its slab [slab_lo, slab_hi) (use
  * +-1e300 for the outermost faces) and passes only the particles inside its slab to set_fluid (ids = global indices).
  * All ranks must share config.domain_min/max.  dfsph_b200_step then also performs: migration of particles that left
  * the slab, the one-support-radius ghost exchange (x, v once per step; kappa and the pressure acceleration once per
- * solver iteration) over NCCL send/recv, and the all-reduce of the density-error sum, the particle count and the CFL
+ * solver iteration, overlapped with the interior computation on a second stream) over NCCL send/recv, and the all-reduce of the density-error sum, the particle count and the CFL
  * maximum, so that every rank takes identical iteration and time-step decisions.  by_id transfers and step_host are
  * not available in multi-GPU runs (download with by_id = 0 together with DFSPH_B200_FIELD_ID). */
-int dfsph_b200_comm_get_unique_id(void* id128);
-int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id128, int rank, int world_size, double slab_lo, double slab_hi);
+int dfsph_b200_comm_get_unique_id(void* id256);   /* 256 bytes: two NCCL ids (reductions/migration + halo refresh) */
+int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id256, int rank, int world_size, double slab_lo, double slab_hi);
 
 /* Device timing.  timer_start/stop bracket any number of calls with two CUDA events on the context's own stream
  * (the stream every kernel of this library is launched on).  With profiling on, every launch of the kernel classes

@@ -82,7 +82,14 @@ struct dfsph_b200_ctx {
     bool has_left = false, has_right = false;
     double slab_lo = -1e300, slab_hi = 1e300;
     NcclApi nccl;
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr, comm2 = nullptr;      // comm: reductions, counts, migration (main stream); comm2: halo refresh (stream2)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_a2 = nullptr, ev_k = nullptr, ev_k2 = nullptr;
+    unsigned *exp_all = nullptr; unsigned n_exp_all = 0;
+    int dbg_skip = 0;      // timing experiments only (DFSPH_B200_DEBUG_SKIP bit 1: ghost refresh inside iterations, bit 2: error all-reduce)
+    bool overlap = true;   // boundary-first overlap of the halo refresh (DFSPH_B200_NO_OVERLAP=1 selects the serial refresh)
+    unsigned char* is_export = nullptr;
+    Real4* ghost_stage = nullptr;
     unsigned ghost_cap = 0, ng = 0, ng_l = 0, ng_r = 0, n_exp_l = 0, n_exp_r = 0;
     unsigned *exp_l = nullptr, *exp_r = nullptr, *gcell_start = nullptr;
     Real4 *send_l = nullptr, *send_r = nullptr, *send_l2 = nullptr, *send_r2 = nullptr;
@@ -341,7 +348,10 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
     cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->send_l); cudaFree(c->send_r);
     cudaFree(c->send_l2); cudaFree(c->send_r2); cudaFree(c->aux_sl); cudaFree(c->aux_sr); cudaFree(c->aux_rl); cudaFree(c->aux_rr);
-    cudaFree(c->xcnt);
+    cudaFree(c->xcnt); cudaFree(c->exp_all); cudaFree(c->is_export); cudaFree(c->ghost_stage);
+    if (c->comm2 && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm2);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_a) { cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_a2); cudaEventDestroy(c->ev_k); cudaEventDestroy(c->ev_k2); }
     if (c->h_xcnt) cudaFreeHost(c->h_xcnt);
     if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
     if (c->h_ctrl) cudaFreeHost(c->h_ctrl);
@@ -544,6 +554,9 @@ static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
         if (dev_alloc(c, &c->aux_rl, gc)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->aux_rr, gc)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->xcnt, 3)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->exp_all, 2 * gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->ghost_stage, gc)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->is_export, cap + gc)) return DFSPH_B200_ERR_CUDA;
         if (!c->h_xcnt) CUDA_TRY(c, cudaMallocHost((void**)&c->h_xcnt, 3 * sizeof(ExchangeCounts)));
         cap += gc;   // owned capacity includes room for arrivals
     }
@@ -570,7 +583,7 @@ static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
     if (dev_alloc(c, &c->tcnt_f, ntiles)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->tcnt_b, ntiles)) return DFSPH_B200_ERR_CUDA;
     { int rs = ensure_scratch(c, cap); if (rs) return rs; }
-    if (dev_alloc(c, &c->partial, div_up(cap, DFSPH_BLOCK) + 1)) return DFSPH_B200_ERR_CUDA;
+    if (dev_alloc(c, &c->partial, 2 * (div_up(cap, DFSPH_BLOCK) + 1))) return DFSPH_B200_ERR_CUDA;
     c->cap = cap;
     return 0;
 }
@@ -812,6 +825,29 @@ static int exchange_ghosts(dfsph_b200_ctx* c, Real4* arr)
     return 0;
 }
 
+// The same refresh on the communication stream (comm2 / stream2): starts once `after` has completed on the main
+// stream, packs the export list of `arr`, receives into `dst` (ghost order: left face first), records `done`.
+static int exchange_ghosts_async(dfsph_b200_ctx* c, const Real4* arr, Real4* dst, cudaEvent_t after, cudaEvent_t done)
+{
+    cudaStream_t s2 = c->stream2;
+    CUDA_TRY(c, cudaStreamWaitEvent(s2, after, 0));
+    const unsigned tot = c->n_exp_l + c->n_exp_r;
+    if (tot > 0) { k_pack_exports<<<div_up(tot, DFSPH_BLOCK), DFSPH_BLOCK, 0, s2>>>(arr, c->exp_l, c->n_exp_l, c->exp_r, c->n_exp_r, c->send_l, c->send_r); c->launches++; }
+    const size_t e = sizeof(Real4);
+    NCCL_TRY(c, c->nccl.GroupStart());
+    if (c->has_left) {
+        NCCL_TRY(c, c->nccl.Send(c->send_l, (size_t)c->n_exp_l * e, ncclChar, c->rank - 1, c->comm2, s2));
+        NCCL_TRY(c, c->nccl.Recv(dst, (size_t)c->ng_l * e, ncclChar, c->rank - 1, c->comm2, s2));
+    }
+    if (c->has_right) {
+        NCCL_TRY(c, c->nccl.Send(c->send_r, (size_t)c->n_exp_r * e, ncclChar, c->rank + 1, c->comm2, s2));
+        NCCL_TRY(c, c->nccl.Recv(dst + c->ng_l, (size_t)c->ng_r * e, ncclChar, c->rank + 1, c->comm2, s2));
+    }
+    NCCL_TRY(c, c->nccl.GroupEnd());
+    CUDA_TRY(c, cudaEventRecord(done, s2));
+    return 0;
+}
+
 // Simulation::performNeighborhoodSearch: sort + reorder + neighbour table
 static int run_search(dfsph_b200_ctx* c)
 {
@@ -883,11 +919,11 @@ static int run_search(dfsph_b200_ctx* c)
         k_zero_counts<<<1, 1, 0, st>>>(c->xcnt);
         const double width = 1.0 / c->grid.inv_cell;
         if (n > 0) k_select_exports<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->pos[c->cur_pos], c->slab_lo, c->slab_hi, width,
-            c->has_left, c->has_right, c->ghost_cap, c->exp_l, c->exp_r, c->xcnt);
+            c->has_left, c->has_right, c->ghost_cap, c->exp_l, c->exp_r, c->exp_all, c->is_export, c->xcnt);
         c->launches += 2;
         rc = exchange_counts(c);
         if (rc) return rc;
-        c->n_exp_l = c->h_xcnt[0].exp_l; c->n_exp_r = c->h_xcnt[0].exp_r;
+        c->n_exp_l = c->h_xcnt[0].exp_l; c->n_exp_r = c->h_xcnt[0].exp_r; c->n_exp_all = c->h_xcnt[0].exp_all;
         c->ng_l = c->has_left ? c->h_xcnt[1].exp_r : 0u;
         c->ng_r = c->has_right ? c->h_xcnt[2].exp_l : 0u;
         c->ng = c->ng_l + c->ng_r;
@@ -937,22 +973,70 @@ static int run_solver(dfsph_b200_ctx* c)
     else k_init_sweep<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl); }
     c->launches++;
 
+    auto launch_accel = [&](const unsigned* list, unsigned list_n, const unsigned char* skip, int seq) {
+        const unsigned g = list ? std::max(div_up(list_n, DFSPH_BLOCK), 1u) : grid;
+        const bool keep = c->profiling;
+        if (list) c->profiling = false;   // the small export-list launch is not part of the per-kernel statistics
+        ProfScope ps(c, DFSPH_B200_PROF_ACCEL, seq);
+        c->profiling = keep;
+        k_accel<MODE><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, list, list_n, skip);
+        c->launches++;
+    };
+    auto launch_jacobi = [&](int solve, const unsigned* list, unsigned list_n, const unsigned char* skip, unsigned base, int finalize, int seq) {
+        const unsigned g = list ? std::max(div_up(list_n, DFSPH_BLOCK), 1u) : grid;
+        const bool keep = c->profiling;
+        if (list) c->profiling = false;
+        ProfScope ps(c, solve == SOLVE_DIV ? DFSPH_B200_PROF_JACOBI_DIV : DFSPH_B200_PROF_JACOBI_PRESS, seq);
+        c->profiling = keep;
+        if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize);
+        else k_jacobi<MODE, SOLVE_PRESS><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize);
+        c->launches++;
+    };
+    // multi-GPU: ghost kappa that arrived on the communication stream is moved into pos[n ..] on the main stream
+    auto land_ghost_kappa = [&]() -> int {
+        CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_k2, 0));
+        if (c->ng > 0) { k_copy_real4<<<div_up(c->ng, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(c->ghost_stage, gpos + c->n, c->ng); c->launches++; }
+        return 0;
+    };
+
     auto solve_loop = [&](int solve, unsigned max_it, unsigned& pred) -> int {
         k_solve_begin<<<1, 1, 0, st>>>(c->ctrl, solve);
         c->launches++;
         unsigned launched = 0;
         unsigned batch = std::min(std::max(pred + 1u, 2u), max_it);
         const size_t prof_start = c->prof_recs.size();
+        if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }   // warm-start kappa of the ghosts
+        bool kappa_in_flight = false;
         while (true) {
             for (unsigned b = 0; b < batch; ++b) {
                 const int seq = (int)(launched + b);
-                if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }          // kappa of the ghosts (pos.w)
-                { ProfScope ps(c, DFSPH_B200_PROF_ACCEL, seq); k_accel<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl); }
-                if (multi) { int rg = exchange_ghosts(c, c->acc); if (rg) return rg; }        // pressure acceleration of the ghosts
-                if (solve == SOLVE_DIV) { ProfScope ps(c, DFSPH_B200_PROF_JACOBI_DIV, seq); k_jacobi<MODE, SOLVE_DIV><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial); }
-                else { ProfScope ps(c, DFSPH_B200_PROF_JACOBI_PRESS, seq); k_jacobi<MODE, SOLVE_PRESS><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial); }
-                c->launches += 2;
-                if (multi) {
+                if (!multi) {
+                    launch_accel(nullptr, 0, nullptr, seq);
+                    launch_jacobi(solve, nullptr, 0, nullptr, 0, 1, seq);
+                } else if (!c->overlap) {
+                    // serial refresh: kappa -> pass A -> acceleration -> pass B -> all-reduce
+                    if (seq > 0 && !(c->dbg_skip & 1)) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
+                    launch_accel(nullptr, 0, nullptr, seq);
+                    if (!(c->dbg_skip & 1)) { int rg = exchange_ghosts(c, c->acc); if (rg) return rg; }
+                    launch_jacobi(solve, nullptr, 0, nullptr, 0, 1, seq);
+                    if (!(c->dbg_skip & 2)) NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->err_sum, &c->ctrl->err_sum, 1, ncclDouble, ncclSum, c->comm, st));
+                    if (solve == SOLVE_DIV) k_solve_control<SOLVE_DIV><<<1, 1, 0, st>>>(c->ctrl, sp, c->sph);
+                    else k_solve_control<SOLVE_PRESS><<<1, 1, 0, st>>>(c->ctrl, sp, c->sph);
+                    c->launches++;
+                } else {
+                    // boundary-first: the export particles' results travel while the interior is being computed
+                    if (kappa_in_flight) { int rl = land_ghost_kappa(); if (rl) return rl; }
+                    const unsigned nbB = std::max(div_up(c->n_exp_all, DFSPH_BLOCK), 1u);
+                    if (c->n_exp_all) launch_accel(c->exp_all, c->n_exp_all, nullptr, -1);
+                    CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+                    { int rg = exchange_ghosts_async(c, c->acc, c->acc + c->n, c->ev_a, c->ev_a2); if (rg) return rg; }
+                    launch_accel(nullptr, 0, c->is_export, seq);
+                    CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_a2, 0));
+                    if (c->n_exp_all) launch_jacobi(solve, c->exp_all, c->n_exp_all, nullptr, 0, 0, -1);
+                    CUDA_TRY(c, cudaEventRecord(c->ev_k, st));
+                    { int rg = exchange_ghosts_async(c, gpos, c->ghost_stage, c->ev_k, c->ev_k2); if (rg) return rg; }
+                    kappa_in_flight = true;
+                    launch_jacobi(solve, nullptr, 0, c->is_export, c->n_exp_all ? nbB : 0u, 1, seq);
                     NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->err_sum, &c->ctrl->err_sum, 1, ncclDouble, ncclSum, c->comm, st));
                     if (solve == SOLVE_DIV) k_solve_control<SOLVE_DIV><<<1, 1, 0, st>>>(c->ctrl, sp, c->sph);
                     else k_solve_control<SOLVE_PRESS><<<1, 1, 0, st>>>(c->ctrl, sp, c->sph);
@@ -965,6 +1049,8 @@ static int run_solver(dfsph_b200_ctx* c)
             if (c->h_ctrl->done || launched >= max_it) break;
             batch = std::min(2u, max_it - launched);
         }
+        if (kappa_in_flight) { int rl = land_ghost_kappa(); if (rl) return rl; }   // final kappa of the ghosts for the finaliser
+        else if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
         pred = c->h_ctrl->iter;
         // launches past the converged iteration exited immediately: keep them out of the per-kernel statistics
         for (size_t r = prof_start; r < c->prof_recs.size();) {
@@ -980,7 +1066,6 @@ static int run_solver(dfsph_b200_ctx* c)
         // the reference's iteration is a no-op for an empty model: avg stays 0, one iteration is counted
         int rc = solve_loop(SOLVE_DIV, c->par.max_iterations_v, c->pred_iter_v);
         if (rc) return rc;
-        if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
         ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
         k_div_final<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
     } else {
@@ -998,7 +1083,6 @@ static int run_solver(dfsph_b200_ctx* c)
         int rc = solve_loop(SOLVE_PRESS, c->par.max_iterations, c->pred_iter);
         if (rc) return rc;
     }
-    if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
     Real4* pos_out = c->pos[1 - c->cur_pos];
     { ProfScope ps(c, DFSPH_B200_PROF_PRESS_FINAL); k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out); }
     k_step_end<<<1, 1, 0, st>>>(c->ctrl);
@@ -1319,19 +1403,23 @@ void* dfsph_b200_alloc_pinned(size_t bytes)
 void dfsph_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- multi-GPU ---------------------------------------------------------------------------------------------------
-int dfsph_b200_comm_get_unique_id(void* id128)
+// id256: two NCCL unique ids (one communicator for reductions / counts / migration, one for the halo refresh that
+// runs concurrently on the communication stream)
+int dfsph_b200_comm_get_unique_id(void* id256)
 {
     static NcclApi api;
     std::string err;
-    if (!id128 || !api.load(err)) { g_create_error = err.empty() ? "null argument" : err; return DFSPH_B200_ERR_COMM; }
-    ncclUniqueId id;
-    if (api.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return DFSPH_B200_ERR_COMM; }
+    if (!id256 || !api.load(err)) { g_create_error = err.empty() ? "null argument" : err; return DFSPH_B200_ERR_COMM; }
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-    memcpy(id128, &id, 128);
+    for (int k = 0; k < 2; ++k) {
+        ncclUniqueId id;
+        if (api.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return DFSPH_B200_ERR_COMM; }
+        memcpy((char*)id256 + 128 * k, &id, 128);
+    }
     return DFSPH_B200_OK;
 }
 
-int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128, int rank, int world, double slab_lo, double slab_hi)
+int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128 /* the 256 bytes of comm_get_unique_id */, int rank, int world, double slab_lo, double slab_hi)
 {
     CHECK_CTX(c);
     cudaSetDevice(c->cfg.device);
@@ -1347,7 +1435,17 @@ int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128, int rank, int wor
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     NCCL_TRY(c, c->nccl.CommInitRank(&c->comm, world, id, rank));
+    ncclUniqueId id2;
+    memcpy(&id2, (const char*)id128 + 128, 128);
+    NCCL_TRY(c, c->nccl.CommInitRank(&c->comm2, world, id2, rank));
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_a2, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_k, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_k2, cudaEventDisableTiming));
     c->multi = true;
+    if (const char* e = getenv("DFSPH_B200_NO_OVERLAP")) c->overlap = !(e[0] == '1');
+    if (const char* e = getenv("DFSPH_B200_DEBUG_SKIP")) c->dbg_skip = atoi(e);
     c->rank = rank; c->world = world;
     c->has_left = rank > 0; c->has_right = rank < world - 1;
     c->slab_lo = slab_lo; c->slab_hi = slab_hi;

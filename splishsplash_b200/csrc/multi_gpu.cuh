@@ -45,6 +45,7 @@ struct NcclApi {
 struct ExchangeCounts {
     unsigned leave_l, leave_r;     // owned particles that crossed the left / right slab face
     unsigned exp_l, exp_r;         // owned particles within one cell of the left / right face (ghost exports)
+    unsigned exp_all, pad0, pad1, pad2;   // union of the two export sets (processed first by the solver passes)
 };
 
 // ---- migration --------------------------------------------------------------------------------------------------
@@ -103,13 +104,23 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash_slab(const Real4* __r
 // ---- ghost exports -------------------------------------------------------------------------------------------------
 // Owned (sorted) particles within `width` of a slab face are exported to that neighbour.
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_select_exports(unsigned n, const Real4* __restrict__ pos, double lo, double hi, double width,
-    int has_left, int has_right, unsigned cap, unsigned* __restrict__ exp_l, unsigned* __restrict__ exp_r, ExchangeCounts* cnt)
+    int has_left, int has_right, unsigned cap, unsigned* __restrict__ exp_l, unsigned* __restrict__ exp_r,
+    unsigned* __restrict__ exp_all, unsigned char* __restrict__ is_export, ExchangeCounts* cnt)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = (double)pos[i].x;
-    if (has_left && x < lo + width) { const unsigned k = atomicAdd(&cnt->exp_l, 1u); if (k < cap) exp_l[k] = i; }
-    if (has_right && x >= hi - width) { const unsigned k = atomicAdd(&cnt->exp_r, 1u); if (k < cap) exp_r[k] = i; }
+    const bool l = has_left && x < lo + width, r = has_right && x >= hi - width;
+    if (l) { const unsigned k = atomicAdd(&cnt->exp_l, 1u); if (k < cap) exp_l[k] = i; }
+    if (r) { const unsigned k = atomicAdd(&cnt->exp_r, 1u); if (k < cap) exp_r[k] = i; }
+    if (l || r) { const unsigned k = atomicAdd(&cnt->exp_all, 1u); if (k < 2u * cap) exp_all[k] = i; }
+    is_export[i] = (l || r) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_copy_real4(const Real4* __restrict__ src, Real4* __restrict__ dst, unsigned n)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) st_real4(dst + k, ld_plain(src + k));
 }
 
 // gather one Real4 field of the export lists into the two send buffers
@@ -128,4 +139,4 @@ __global__ void k_write_sentinel(Real4* pos, Real4* vel, Real4* acc, unsigned at
     st_real4(acc + at, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
 }
 
-__global__ void k_zero_counts(ExchangeCounts* c) { c->leave_l = c->leave_r = c->exp_l = c->exp_r = 0u; }
+__global__ void k_zero_counts(ExchangeCounts* c) { c->leave_l = c->leave_r = c->exp_l = c->exp_r = c->exp_all = 0u; }

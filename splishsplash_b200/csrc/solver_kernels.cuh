@@ -268,12 +268,17 @@ __device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphCo
 
 // Non-active particles (emitter-animated / fixed) keep a zero pressure acceleration; their lanes still walk the
 // warp-uniform loop (results discarded) so that the sweep stays convergent.
+// Multi-GPU overlap: the particles a neighbour rank needs (export list) are processed first by a launch over `list`,
+// their values travel on the communication stream while a second launch over all particles skips them (`skip`).
+// Single GPU: list == nullptr, skip == nullptr.
 template <int MODE>
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_accel(FluidArrays f, SphConst c, const Ctrl* __restrict__ ctrl)
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_accel(FluidArrays f, SphConst c, const Ctrl* __restrict__ ctrl,
+                                                         const unsigned* __restrict__ list, unsigned list_n, const unsigned char* __restrict__ skip)
 {
     if (ctrl->done) return;
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= f.n) return;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) { if (i >= list_n) return; i = list[i]; }
+    else { if (i >= f.n) return; if (skip && skip[i]) return; }
     Real ax, ay, az;
     const Real4 xi = ld_gather(f.pos + i);
     pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
@@ -328,13 +333,20 @@ __device__ __forceinline__ void solve_control(Ctrl* ctrl, const SolverParams& sp
     ctrl->done = cont ? 0 : 1;
 }
 
+// list / skip: see k_accel.  partial_base: first slot of this launch in `partial`; finalize: this launch elects the last
+// block, which sums partial[0 .. partial_base + gridDim.x) (the export-list launch runs first with finalize = 0).
 template <int MODE, int SOLVE>
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial)
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial,
+                                                          const unsigned* __restrict__ list, unsigned list_n, const unsigned char* __restrict__ skip,
+                                                          unsigned partial_base, int finalize)
 {
     if (ctrl->done) return;
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active;
+    if (list) { active = i < list_n; if (active) i = list[i]; }
+    else active = i < f.n && !(skip && skip[i]);
     double err = 0.0;
-    if (i < f.n) {
+    if (active) {
         const Real h = ctrl->h;
         const Real4 xi = ld_plain(f.pos + i);
         const Real4 ai = ld_gather(f.acc + i);
@@ -361,10 +373,11 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst 
     }
     // density-error reduction: block partials, summed in fixed order by the last block (deterministic)
     const double bsum = block_sum_double(err);
-    if (threadIdx.x == 0) partial[blockIdx.x] = bsum;
+    if (threadIdx.x == 0) partial[partial_base + blockIdx.x] = bsum;
+    if (!finalize) return;
     if (last_block(ctrl)) {
         double t = 0.0;
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += partial[b];
+        for (unsigned b = threadIdx.x; b < partial_base + gridDim.x; b += blockDim.x) t += partial[b];
         t = block_sum_double(t);
         if (threadIdx.x == 0) {
             ctrl->err_sum = t;

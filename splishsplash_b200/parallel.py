@@ -62,15 +62,15 @@ def select_slab(scene, rank: int, world: int, bounds=None, halo_cells: float = 2
 
 def bootstrap_comm(ts, rank: int, world: int, slab):
     """Create the NCCL communicator of a TimeStepDFSPH_B200 context: rank 0 draws the unique id, torch.distributed
-    broadcasts the 128 bytes, every rank calls dfsph_b200_comm_init.  Must run before set_fluid."""
+    broadcasts the 256 bytes, every rank calls dfsph_b200_comm_init.  Must run before set_fluid."""
     import torch.distributed as dist
-    buf = (C.c_char * 128)()
+    buf = (C.c_char * 256)()
     if rank == 0:
         ts._check(ts.lib.dfsph_b200_comm_get_unique_id(buf))
     obj = [bytes(buf.raw) if rank == 0 else None]
     if world > 1:
         dist.broadcast_object_list(obj, src=0)
-    idb = (C.c_char * 128).from_buffer_copy(obj[0])
+    idb = (C.c_char * 256).from_buffer_copy(obj[0])
     ts._check(ts.lib.dfsph_b200_comm_init(ts.ctx, idb, rank, world, float(slab[0]), float(slab[1])))
 
 
