@@ -184,6 +184,18 @@ int dfsph_b200_eval_kernel(dfsph_b200_ctx* ctx, int kernel, uint64_t n, const vo
 int dfsph_b200_comm_get_unique_id(void* id256);   /* 256 bytes: two NCCL ids (reductions/migration + halo refresh) */
 int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id256, int rank, int world_size, double slab_lo, double slab_hi);
 
+/* Optional: refresh the ghost particles with direct NVLink peer stores instead of NCCL send/recv.  After set_fluid
+ * every rank exports a 512-byte blob of CUDA IPC handles (its particle arrays, flag words and all-reduce table), the
+ * host layer all-gathers the blobs and hands every rank the full set, and from then on (a) every ghost refresh is one
+ * small kernel that stores the export values straight into the neighbour's ghost slots and publishes a sequence number
+ * there -- the consumer kernel spins on its local flag at its start -- and (b) the per-iteration all-reduce of the
+ * density error is fused into the tail of pass B: every rank stores its partial sum into every rank's table, waits for
+ * all of them and adds them up in rank order.  A solver iteration is then 4 kernel launches and no NCCL call.
+ * Requires peer access between the GPUs (NVLink/NVSwitch), at most 16 ranks; if p2p_import is never called the NCCL
+ * path is used. */
+int dfsph_b200_p2p_export(dfsph_b200_ctx* ctx, void* blob512);
+int dfsph_b200_p2p_import(dfsph_b200_ctx* ctx, const void* blobs_all /* world_size x 512 bytes, in rank order */);
+
 /* Device timing.  timer_start/stop bracket any number of calls with two CUDA events on the context's own stream
  * (the stream every kernel of this library is launched on).  With profiling on, every launch of the kernel classes
  * below is additionally bracketed by its own event pair; get_profile returns accumulated milliseconds and launch

@@ -145,6 +145,8 @@ struct Ctrl {
     unsigned max_nbr;
     unsigned multi;         // 1: multi-GPU run, loop control happens in k_solve_control after the all-reduce
     unsigned long long n_global;   // particles of all ranks (divisor of the average density error)
+    unsigned red_seq;       // sequence number of the fused peer-memory all-reduce
+    unsigned pad1;
 };
 
 struct SolverParams {

@@ -87,6 +87,15 @@ struct dfsph_b200_ctx {
     cudaEvent_t ev_a = nullptr, ev_a2 = nullptr, ev_k = nullptr, ev_k2 = nullptr;
     unsigned *exp_all = nullptr; unsigned n_exp_all = 0;
     int dbg_skip = 0;      // timing experiments only (DFSPH_B200_DEBUG_SKIP bit 1: ghost refresh inside iterations, bit 2: error all-reduce)
+    // NVLink P2P ghost refresh (peer buffers mapped through CUDA IPC)
+    bool p2p = false;
+    unsigned* flags = nullptr;          // [3 arrays][2 sides] sequence numbers written by the neighbours; [6] = push ticket
+    unsigned seq[3] = {0, 0, 0};
+    struct Peer { Real4* pos[2] = {nullptr, nullptr}; Real4* vel[2] = {nullptr, nullptr}; Real4* acc = nullptr; unsigned* flags = nullptr; bool open = false; } peer[2];
+    unsigned peer_n[2] = {0, 0}, peer_ngl[2] = {0, 0};
+    double* red_val = nullptr; unsigned* red_seq = nullptr;     // my all-reduce table: val [2][MAX_RANKS], seq [MAX_RANKS]
+    PeerReduce pr;                                              // every rank's table (peer-mapped)
+    std::vector<void*> red_opened;
     bool overlap = true;   // boundary-first overlap of the halo refresh (DFSPH_B200_NO_OVERLAP=1 selects the serial refresh)
     unsigned char* is_export = nullptr;
     Real4* ghost_stage = nullptr;
@@ -348,6 +357,12 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
     cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->send_l); cudaFree(c->send_r);
     cudaFree(c->send_l2); cudaFree(c->send_r2); cudaFree(c->aux_sl); cudaFree(c->aux_sr); cudaFree(c->aux_rl); cudaFree(c->aux_rr);
+    for (int s = 0; s < 2; ++s) if (c->peer[s].open) {
+        for (int b = 0; b < 2; ++b) { cudaIpcCloseMemHandle(c->peer[s].pos[b]); cudaIpcCloseMemHandle(c->peer[s].vel[b]); }
+        cudaIpcCloseMemHandle(c->peer[s].acc); cudaIpcCloseMemHandle(c->peer[s].flags);
+    }
+    for (void* p : c->red_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c->flags); cudaFree(c->red_val); cudaFree(c->red_seq);
     cudaFree(c->xcnt); cudaFree(c->exp_all); cudaFree(c->is_export); cudaFree(c->ghost_stage);
     if (c->comm2 && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm2);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -805,9 +820,49 @@ static int exchange_counts(dfsph_b200_ctx* c)
 }
 
 // refresh one Real4 field of the ghost particles from the owning ranks (ghost slots [n, n+ng) of `arr`)
+enum { GH_POS = 0, GH_VEL = 1, GH_ACC = 2 };
+
+// P2P version: push the export values into the neighbours' ghost slots, then wait for theirs
+static int p2p_refresh(dfsph_b200_ctx* c, int kind, bool wait = true)
+{
+    cudaStream_t st = c->stream;
+    const Real4* src = kind == GH_POS ? c->pos[c->cur_pos] : (kind == GH_VEL ? c->vel[c->cur] : c->acc);
+    auto peer_arr = [&](int side) -> Real4* {
+        const dfsph_b200_ctx::Peer& p = c->peer[side];
+        return kind == GH_POS ? p.pos[c->cur_pos] : (kind == GH_VEL ? p.vel[c->cur] : p.acc);
+    };
+    const unsigned seq = ++c->seq[kind];
+    // my exports to the left neighbour are ITS right ghosts (behind its left ghosts); to the right neighbour its left ghosts
+    Real4* dst_l = c->has_left ? peer_arr(0) + c->peer_n[0] + c->peer_ngl[0] : nullptr;
+    Real4* dst_r = c->has_right ? peer_arr(1) + c->peer_n[1] : nullptr;
+    unsigned* flag_l = c->has_left ? c->peer[0].flags + kind * 2 + 1 : nullptr;    // I am the left neighbour's RIGHT side
+    unsigned* flag_r = c->has_right ? c->peer[1].flags + kind * 2 + 0 : nullptr;   // and the right neighbour's LEFT side
+    const unsigned tot = c->n_exp_l + c->n_exp_r;
+    k_push_exports<<<std::max(div_up(tot, DFSPH_BLOCK), 1u), DFSPH_BLOCK, 0, st>>>(src, c->exp_l, c->n_exp_l, dst_l, flag_l,
+        c->exp_r, c->n_exp_r, dst_r, flag_r, seq, c->flags + 6);
+    c->launches++;
+    if (wait) {
+        k_wait_flags<<<1, 1, 0, st>>>(c->has_left ? c->flags + kind * 2 + 0 : nullptr, c->has_right ? c->flags + kind * 2 + 1 : nullptr, seq);
+        c->launches++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+// what a consumer kernel has to see before it reads the ghost values of `kind` (fused wait at kernel start)
+static GhostWait ghost_wait_args(const dfsph_b200_ctx* c, int kind)
+{
+    GhostWait w;
+    w.left = (c->p2p && c->has_left) ? c->flags + kind * 2 + 0 : nullptr;
+    w.right = (c->p2p && c->has_right) ? c->flags + kind * 2 + 1 : nullptr;
+    w.seq = c->seq[kind];
+    return w;
+}
+
 static int exchange_ghosts(dfsph_b200_ctx* c, Real4* arr)
 {
     if (!c->multi) return 0;
+    if (c->p2p) return p2p_refresh(c, arr == c->acc ? GH_ACC : (arr == c->vel[c->cur] ? GH_VEL : GH_POS));
     cudaStream_t st = c->stream;
     const unsigned tot = c->n_exp_l + c->n_exp_r;
     if (tot > 0) { k_pack_exports<<<div_up(tot, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(arr, c->exp_l, c->n_exp_l, c->exp_r, c->n_exp_r, c->send_l, c->send_r); c->launches++; }
@@ -905,11 +960,11 @@ static int run_search(dfsph_b200_ctx* c)
         if (rc) return rc;
     }
     c->ng = c->ng_l = c->ng_r = 0;
-    if (n > 0) {
+    if (n > 0 || c->multi) {   // multi-GPU: every rank flips its buffers every step (peers address them by parity)
         const int src = c->cur, dst = 1 - c->cur;
         const int psrc = c->cur_pos, pdst = 1 - c->cur_pos;
         ProfScope ps(c, DFSPH_B200_PROF_SORT);
-        k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
+        if (n > 0) k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
             c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc);
         c->cur = dst; c->cur_pos = pdst;
         c->launches++;
@@ -929,6 +984,16 @@ static int run_search(dfsph_b200_ctx* c)
         c->ng = c->ng_l + c->ng_r;
         if (c->n_exp_l > c->ghost_cap || c->n_exp_r > c->ghost_cap || c->ng > c->ghost_cap)
             CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "ghost buffers too small (export %u/%u, ghosts %u, capacity %u)", c->n_exp_l, c->n_exp_r, c->ng, c->ghost_cap);
+        if (c->p2p) {
+            // the peers' owned counts and left-ghost counts locate my slots inside their ghost regions
+            ExchangeCounts mine = c->h_xcnt[0];
+            mine.pad0 = n; mine.pad1 = c->ng_l;
+            CUDA_TRY(c, cudaMemcpyAsync(c->xcnt, &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+            rc = exchange_counts(c);
+            if (rc) return rc;
+            c->peer_n[0] = c->h_xcnt[1].pad0; c->peer_ngl[0] = c->h_xcnt[1].pad1;
+            c->peer_n[1] = c->h_xcnt[2].pad0; c->peer_ngl[1] = c->h_xcnt[2].pad1;
+        }
         rc = exchange_ghosts(c, c->pos[c->cur_pos]); if (rc) return rc;
         rc = exchange_ghosts(c, c->vel[c->cur]); if (rc) return rc;
         k_write_sentinel<<<1, 1, 0, st>>>(c->pos[c->cur_pos], c->vel[c->cur], c->acc, n + c->ng);
@@ -973,23 +1038,26 @@ static int run_solver(dfsph_b200_ctx* c)
     else k_init_sweep<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl); }
     c->launches++;
 
-    auto launch_accel = [&](const unsigned* list, unsigned list_n, const unsigned char* skip, int seq) {
+    PeerReduce no_red; memset(&no_red, 0, sizeof(no_red));
+    auto launch_accel = [&](const unsigned* list, unsigned list_n, const unsigned char* skip, int seq, GhostWait gw = GhostWait{nullptr, nullptr, 0u}) {
         const unsigned g = list ? std::max(div_up(list_n, DFSPH_BLOCK), 1u) : grid;
         const bool keep = c->profiling;
         if (list) c->profiling = false;   // the small export-list launch is not part of the per-kernel statistics
         ProfScope ps(c, DFSPH_B200_PROF_ACCEL, seq);
         c->profiling = keep;
-        k_accel<MODE><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, list, list_n, skip);
+        k_accel<MODE><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, list, list_n, skip, gw);
         c->launches++;
     };
-    auto launch_jacobi = [&](int solve, const unsigned* list, unsigned list_n, const unsigned char* skip, unsigned base, int finalize, int seq) {
+    auto launch_jacobi = [&](int solve, const unsigned* list, unsigned list_n, const unsigned char* skip, unsigned base, int finalize, int seq,
+                             GhostWait gw = GhostWait{nullptr, nullptr, 0u}, const PeerReduce* prp = nullptr) {
+        const PeerReduce& pr = prp ? *prp : no_red;
         const unsigned g = list ? std::max(div_up(list_n, DFSPH_BLOCK), 1u) : grid;
         const bool keep = c->profiling;
         if (list) c->profiling = false;
         ProfScope ps(c, solve == SOLVE_DIV ? DFSPH_B200_PROF_JACOBI_DIV : DFSPH_B200_PROF_JACOBI_PRESS, seq);
         c->profiling = keep;
-        if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize);
-        else k_jacobi<MODE, SOLVE_PRESS><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize);
+        if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize, gw, pr);
+        else k_jacobi<MODE, SOLVE_PRESS><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize, gw, pr);
         c->launches++;
     };
     // multi-GPU: ghost kappa that arrived on the communication stream is moved into pos[n ..] on the main stream
@@ -1006,13 +1074,24 @@ static int run_solver(dfsph_b200_ctx* c)
         unsigned batch = std::min(std::max(pred + 1u, 2u), max_it);
         const size_t prof_start = c->prof_recs.size();
         if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }   // warm-start kappa of the ghosts
-        bool kappa_in_flight = false;
+        bool kappa_in_flight = false, p2p_kappa_pending = false;
         while (true) {
             for (unsigned b = 0; b < batch; ++b) {
                 const int seq = (int)(launched + b);
                 if (!multi) {
                     launch_accel(nullptr, 0, nullptr, seq);
                     launch_jacobi(solve, nullptr, 0, nullptr, 0, 1, seq);
+                } else if (c->p2p) {
+                    // peer-memory path, no NCCL call per iteration: a small kernel pushes the export values over NVLink and
+                    // a one-thread kernel waits for the neighbours' flags (a per-block acquire at the start of the big
+                    // kernels was measured slower: system-scope acquires flush the SM's L1); pass B ends with the fused
+                    // all-reduce + loop control
+                    if (seq > 0) { const GhostWait w = ghost_wait_args(c, GH_POS); k_wait_flags<<<1, 1, 0, st>>>(w.left, w.right, w.seq); c->launches++; }
+                    launch_accel(nullptr, 0, nullptr, seq);
+                    { int rg = p2p_refresh(c, GH_ACC, true); if (rg) return rg; }
+                    launch_jacobi(solve, nullptr, 0, nullptr, 0, 1, seq, GhostWait{nullptr, nullptr, 0u}, &c->pr);
+                    { int rg = p2p_refresh(c, GH_POS, false); if (rg) return rg; }
+                    p2p_kappa_pending = true;
                 } else if (!c->overlap) {
                     // serial refresh: kappa -> pass A -> acceleration -> pass B -> all-reduce
                     if (seq > 0 && !(c->dbg_skip & 1)) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
@@ -1050,6 +1129,11 @@ static int run_solver(dfsph_b200_ctx* c)
             batch = std::min(2u, max_it - launched);
         }
         if (kappa_in_flight) { int rl = land_ghost_kappa(); if (rl) return rl; }   // final kappa of the ghosts for the finaliser
+        else if (p2p_kappa_pending) {
+            const GhostWait w = ghost_wait_args(c, GH_POS);
+            k_wait_flags<<<1, 1, 0, st>>>(w.left, w.right, w.seq);
+            c->launches++;
+        }
         else if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
         pred = c->h_ctrl->iter;
         // launches past the converged iteration exited immediately: keep them out of the per-kernel statistics
@@ -1451,6 +1535,70 @@ int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128 /* the 256 bytes o
     c->slab_lo = slab_lo; c->slab_hi = slab_hi;
     const unsigned one = 1u;
     CUDA_TRY(c, cudaMemcpy(&c->ctrl->multi, &one, sizeof(one), cudaMemcpyHostToDevice));
+    return DFSPH_B200_OK;
+}
+
+// P2P blob layout: 8 cudaIpcMemHandle_t (pos[0], pos[1], vel[0], vel[1], acc, flags, reduce values, reduce sequence words) = 512 bytes
+int dfsph_b200_p2p_export(dfsph_b200_ctx* c, void* blob512)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!blob512) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "null blob");
+    if (!c->multi || c->cap == 0) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "call comm_init and set_fluid first");
+    if (!c->flags) { if (dev_alloc(c, &c->flags, 8)) return DFSPH_B200_ERR_CUDA; CUDA_TRY(c, cudaMemset(c->flags, 0, 8 * sizeof(unsigned))); }
+    memset(blob512, 0, 512);
+    cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)blob512;
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[0], c->pos[0]));
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[1], c->pos[1]));
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[2], c->vel[0]));
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[3], c->vel[1]));
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[4], c->acc));
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[5], c->flags));
+    if (!c->red_val) {
+        if (dev_alloc(c, &c->red_val, 2 * DFSPH_MAX_RANKS)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->red_seq, DFSPH_MAX_RANKS)) return DFSPH_B200_ERR_CUDA;
+        CUDA_TRY(c, cudaMemset(c->red_val, 0, 2 * DFSPH_MAX_RANKS * sizeof(double)));
+        CUDA_TRY(c, cudaMemset(c->red_seq, 0, DFSPH_MAX_RANKS * sizeof(unsigned)));
+    }
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[6], c->red_val));
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h[7], c->red_seq));
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_p2p_import(dfsph_b200_ctx* c, const void* blobs_all)
+{
+    CHECK_CTX(c);
+    cudaSetDevice(c->cfg.device);
+    if (!c->multi || !c->flags) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "call p2p_export first");
+    if (!blobs_all) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "null blobs");
+    if (c->world > DFSPH_MAX_RANKS) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "peer-memory path supports up to %d ranks", DFSPH_MAX_RANKS);
+    const char* all = (const char*)blobs_all;
+    const void* blobs[2] = { c->has_left ? all + 512 * (c->rank - 1) : nullptr, c->has_right ? all + 512 * (c->rank + 1) : nullptr };
+    // all-to-all tables of the fused density-error all-reduce
+    memset(&c->pr, 0, sizeof(c->pr));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) { c->pr.val[r] = c->red_val; c->pr.seq[r] = c->red_seq; continue; }
+        const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)(all + 512 * r);
+        void *pv = nullptr, *ps = nullptr;
+        CUDA_TRY(c, cudaIpcOpenMemHandle(&pv, h[6], cudaIpcMemLazyEnablePeerAccess));
+        CUDA_TRY(c, cudaIpcOpenMemHandle(&ps, h[7], cudaIpcMemLazyEnablePeerAccess));
+        c->red_opened.push_back(pv); c->red_opened.push_back(ps);
+        c->pr.val[r] = (double*)pv; c->pr.seq[r] = (unsigned*)ps;
+    }
+    c->pr.rank = c->rank; c->pr.world = c->world;
+    for (int s = 0; s < 2; ++s) {
+        const bool need = s == 0 ? c->has_left : c->has_right;
+        if (!need) continue;
+        if (!blobs[s]) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "missing neighbour blob");
+        const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)blobs[s];
+        void* p[6];
+        for (int k = 0; k < 6; ++k) CUDA_TRY(c, cudaIpcOpenMemHandle(&p[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+        c->peer[s].pos[0] = (Real4*)p[0]; c->peer[s].pos[1] = (Real4*)p[1];
+        c->peer[s].vel[0] = (Real4*)p[2]; c->peer[s].vel[1] = (Real4*)p[3];
+        c->peer[s].acc = (Real4*)p[4]; c->peer[s].flags = (unsigned*)p[5];
+        c->peer[s].open = true;
+    }
+    c->p2p = true;
     return DFSPH_B200_OK;
 }
 

@@ -19,6 +19,27 @@
 
 #define DFSPH_EPS ((Real)1.0e-5)   /* TimeStepDFSPH::m_eps, TimeStepDFSPH.h:28 */
 
+// Multi-GPU with peer memory: flags the kernel has to see before it may read ghost values, and the all-to-all table of
+// the fused density-error all-reduce (every rank stores its partial sum into every rank's table over NVLink).
+#define DFSPH_MAX_RANKS 16
+struct GhostWait { const unsigned* left; const unsigned* right; unsigned seq; };
+struct PeerReduce {
+    double* val[DFSPH_MAX_RANKS];      // val[r]: table of rank r (device pointer, peer-mapped), layout [2 parities][DFSPH_MAX_RANKS]
+    unsigned* seq[DFSPH_MAX_RANKS];    // seq[r]: sequence words of rank r, layout [DFSPH_MAX_RANKS]
+    int rank, world;                   // world == 0: not in use
+};
+
+__device__ __forceinline__ void ghost_wait(const GhostWait& w)
+{
+    if (w.left == nullptr && w.right == nullptr) return;
+    if (threadIdx.x == 0) {
+        unsigned v;
+        if (w.left) do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w.left) : "memory"); } while ((int)(v - w.seq) < 0);
+        if (w.right) do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w.right) : "memory"); } while ((int)(v - w.seq) < 0);
+    }
+    __syncthreads();
+}
+
 struct FluidArrays {
     Real4* pos;          // (x, y, z, kappa of the running solve); element [n] is the far-away sentinel particle
     Real4* vel;          // (vx, vy, vz, -); [n] = 0
@@ -273,9 +294,11 @@ __device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphCo
 // Single GPU: list == nullptr, skip == nullptr.
 template <int MODE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_accel(FluidArrays f, SphConst c, const Ctrl* __restrict__ ctrl,
-                                                         const unsigned* __restrict__ list, unsigned list_n, const unsigned char* __restrict__ skip)
+                                                         const unsigned* __restrict__ list, unsigned list_n, const unsigned char* __restrict__ skip,
+                                                         GhostWait gw)
 {
     if (ctrl->done) return;
+    ghost_wait(gw);     // ghost kappa pushed by the neighbour ranks (no-op on a single GPU)
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (list) { if (i >= list_n) return; i = list[i]; }
     else { if (i >= f.n) return; if (skip && skip[i]) return; }
@@ -338,9 +361,10 @@ __device__ __forceinline__ void solve_control(Ctrl* ctrl, const SolverParams& sp
 template <int MODE, int SOLVE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial,
                                                           const unsigned* __restrict__ list, unsigned list_n, const unsigned char* __restrict__ skip,
-                                                          unsigned partial_base, int finalize)
+                                                          unsigned partial_base, int finalize, GhostWait gw, PeerReduce pr)
 {
     if (ctrl->done) return;
+    ghost_wait(gw);     // ghost pressure accelerations pushed by the neighbour ranks
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active;
     if (list) { active = i < list_n; if (active) i = list[i]; }
@@ -379,7 +403,33 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_jacobi(FluidArrays f, SphConst 
         double t = 0.0;
         for (unsigned b = threadIdx.x; b < partial_base + gridDim.x; b += blockDim.x) t += partial[b];
         t = block_sum_double(t);
-        if (threadIdx.x == 0) {
+        if (pr.world > 0) {
+            // fused all-reduce over peer memory: publish my partial sum in every rank's table, wait for everybody's,
+            // add them up in rank order (bitwise identical on all ranks), then take the loop decision right here
+            __shared__ double my_sum;
+            __shared__ unsigned red_seq;
+            if (threadIdx.x == 0) { my_sum = t; red_seq = ctrl->red_seq + 1u; }
+            __syncthreads();
+            const unsigned s = red_seq, par = s & 1u;
+            if ((int)threadIdx.x < pr.world) {
+                const int r = threadIdx.x;
+                pr.val[r][par * DFSPH_MAX_RANKS + pr.rank] = my_sum;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(pr.seq[r] + pr.rank), "r"(s) : "memory");
+                unsigned v;
+                do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pr.seq[pr.rank] + r) : "memory"); } while ((int)(v - s) < 0);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                double g = 0.0;
+                const volatile double* mine = pr.val[pr.rank] + par * DFSPH_MAX_RANKS;
+                for (int r = 0; r < pr.world; ++r) g += mine[r];
+                ctrl->err_sum = g;
+                ctrl->red_seq = s;
+                solve_control<SOLVE>(ctrl, sp, c, ctrl->n_global);
+            }
+        } else if (threadIdx.x == 0) {
             ctrl->err_sum = t;
             if (!ctrl->multi) solve_control<SOLVE>(ctrl, sp, c, (unsigned long long)f.n);
         }

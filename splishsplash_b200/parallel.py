@@ -74,7 +74,19 @@ def bootstrap_comm(ts, rank: int, world: int, slab):
     ts._check(ts.lib.dfsph_b200_comm_init(ts.ctx, idb, rank, world, float(slab[0]), float(slab[1])))
 
 
-def build_b200_slab(scene_rank, precision, rank, world, kernel=4, device=0, boundary_V=None, **params):
+def enable_p2p(ts, rank: int, world: int):
+    """Switch the ghost refresh of a slab context to direct NVLink peer stores: all_gather the CUDA IPC blobs and hand
+    every rank its neighbours'.  Must run after set_fluid (the buffers must exist)."""
+    import torch.distributed as dist
+    blob = (C.c_char * 512)()
+    ts._check(ts.lib.dfsph_b200_p2p_export(ts.ctx, blob))
+    blobs = [None] * world
+    dist.all_gather_object(blobs, bytes(blob.raw))
+    allb = (C.c_char * (512 * world)).from_buffer_copy(b"".join(blobs))
+    ts._check(ts.lib.dfsph_b200_p2p_import(ts.ctx, allb))
+
+
+def build_b200_slab(scene_rank, precision, rank, world, kernel=4, device=0, boundary_V=None, p2p=None, **params):
     """TimeStepDFSPH_B200 for one rank of a slab-decomposed scene (see select_slab)."""
     from .solver import TimeStepDFSPH_B200
     ts = TimeStepDFSPH_B200(precision, scene_rank["radius"], kernel, device=device, domain=scene_rank["domain"])
@@ -87,4 +99,9 @@ def build_b200_slab(scene_rank, precision, rank, world, kernel=4, device=0, boun
         ts.add_boundary(bx, boundary_V)
         if boundary_V is None:
             ts.compute_boundary_volume()
+    import os
+    if p2p is None:
+        p2p = os.environ.get("DFSPH_B200_P2P", "1") != "0"
+    if p2p and world > 1:
+        enable_p2p(ts, rank, world)
     return ts
