@@ -171,10 +171,10 @@ uint64_t dfsph_b200_num_boundary_particles(const dfsph_b200_ctx* ctx);
  * Lets the reference's Tests/Kernel/KernelTests.cpp checks run against the device implementations. */
 int dfsph_b200_eval_kernel(dfsph_b200_ctx* ctx, int kernel, uint64_t n, const void* r, void* W, void* gradW);
 
-/* ---- multi-GPU slab decomposition along x: one context per GPU / process (DESIGN.md "Multi-GPU") -------------------
+/* ---- multi-GPU slab decomposition along one axis (0 x, 1 y, 2 z): one context per GPU / process (DESIGN.md "Multi-GPU") -------------------
  * The reference has no distributed path at all; these entry points are new.  Rank 0 obtains an id with
  * dfsph_b200_comm_get_unique_id and hands the 256 bytes to every rank (the host layer uses torch.distributed for
- * that); every rank then calls dfsph_b200_comm_init BEFORE dfsph_b200_set_fluid with its slab [slab_lo, slab_hi) (use
+ * that); every rank then calls dfsph_b200_comm_init BEFORE dfsph_b200_set_fluid with the slab axis and its slab [slab_lo, slab_hi) (use
  * +-1e300 for the outermost faces) and passes only the particles inside its slab to set_fluid (ids = global indices).
  * All ranks must share config.domain_min/max.  dfsph_b200_step then also performs: migration of particles that left
  * the slab, the one-support-radius ghost exchange (x, v once per step; kappa and the pressure acceleration once per
@@ -182,7 +182,7 @@ int dfsph_b200_eval_kernel(dfsph_b200_ctx* ctx, int kernel, uint64_t n, const vo
  * maximum, so that every rank takes identical iteration and time-step decisions.  by_id transfers and step_host are
  * not available in multi-GPU runs (download with by_id = 0 together with DFSPH_B200_FIELD_ID). */
 int dfsph_b200_comm_get_unique_id(void* id256);   /* 256 bytes: two NCCL ids (reductions/migration + halo refresh) */
-int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id256, int rank, int world_size, double slab_lo, double slab_hi);
+int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id256, int rank, int world_size, int axis, double slab_lo, double slab_hi);
 
 /* Optional: refresh the ghost particles with direct NVLink peer stores instead of NCCL send/recv.  After set_fluid
  * every rank exports a 512-byte blob of CUDA IPC handles (its particle arrays, flag words and all-reduce table), the

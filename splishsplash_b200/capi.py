@@ -118,7 +118,7 @@ def load(precision: str = "f32"):
     L.dfsph_b200_timer_start.argtypes = [P]
     L.dfsph_b200_timer_stop.argtypes = [P, C.POINTER(C.c_float)]
     L.dfsph_b200_comm_get_unique_id.argtypes = [P]
-    L.dfsph_b200_comm_init.argtypes = [P, P, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.dfsph_b200_comm_init.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
     L.dfsph_b200_p2p_export.argtypes = [P, P]
     L.dfsph_b200_p2p_import.argtypes = [P, P]
     want = 4 if precision == "f32" else 8

@@ -81,6 +81,7 @@ struct dfsph_b200_ctx {
     int rank = 0, world = 1;
     bool has_left = false, has_right = false;
     double slab_lo = -1e300, slab_hi = 1e300;
+    int slab_axis = 0;
     NcclApi nccl;
     ncclComm_t comm = nullptr, comm2 = nullptr;      // comm: reductions, counts, migration (main stream); comm2: halo refresh (stream2)
     cudaStream_t stream2 = nullptr;
@@ -491,7 +492,7 @@ static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* 
     const unsigned nk = g.num_keys + 1u;   // + dump cell
     CUDA_TRY(c, cudaMemsetAsync(c->cell_count, 0, (size_t)nk * sizeof(unsigned), st));
     if (n > 0) {
-        if (slab) k_cell_hash_slab<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->slab_lo, c->slab_hi, c->has_left, c->has_right,
+        if (slab) k_cell_hash_slab<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->slab_lo, c->slab_hi, c->slab_axis, c->has_left, c->has_right,
                                                                                    c->cell_count, c->cell_key, c->cell_rank, c->cell_fine);
         else k_cell_hash<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(pos, n, g, c->cell_count, c->cell_key, c->cell_rank, c->cell_fine);
         c->launches++;
@@ -913,7 +914,7 @@ static int run_search(dfsph_b200_ctx* c)
         // ---- particle migration: owned particles that left the slab go to the neighbour rank --------------------------
         k_zero_counts<<<1, 1, 0, st>>>(c->xcnt);
         if (n > 0) k_pack_leavers<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->pos[c->cur_pos], c->vel[c->cur], c->kappa[c->cur], c->kappa_v[c->cur],
-            c->id[c->cur], c->state[c->cur], c->slab_lo, c->slab_hi, c->has_left, c->has_right, c->ghost_cap,
+            c->id[c->cur], c->state[c->cur], c->slab_lo, c->slab_hi, c->slab_axis, c->has_left, c->has_right, c->ghost_cap,
             c->send_l, c->send_l2, c->aux_sl, c->send_r, c->send_r2, c->aux_sr, c->xcnt);
         c->launches += 2;
         rc = exchange_counts(c);
@@ -973,7 +974,7 @@ static int run_search(dfsph_b200_ctx* c)
         // ---- ghost layer: one cell width of the neighbouring slabs, appended behind the owned particles ---------------
         k_zero_counts<<<1, 1, 0, st>>>(c->xcnt);
         const double width = 1.0 / c->grid.inv_cell;
-        if (n > 0) k_select_exports<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->pos[c->cur_pos], c->slab_lo, c->slab_hi, width,
+        if (n > 0) k_select_exports<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->pos[c->cur_pos], c->slab_lo, c->slab_hi, width, c->slab_axis,
             c->has_left, c->has_right, c->ghost_cap, c->exp_l, c->exp_r, c->exp_all, c->is_export, c->xcnt);
         c->launches += 2;
         rc = exchange_counts(c);
@@ -1503,7 +1504,7 @@ int dfsph_b200_comm_get_unique_id(void* id256)
     return DFSPH_B200_OK;
 }
 
-int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128 /* the 256 bytes of comm_get_unique_id */, int rank, int world, double slab_lo, double slab_hi)
+int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128 /* the 256 bytes of comm_get_unique_id */, int rank, int world, int axis, double slab_lo, double slab_hi)
 {
     CHECK_CTX(c);
     cudaSetDevice(c->cfg.device);
@@ -1513,6 +1514,8 @@ int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128 /* the 256 bytes o
     for (int k = 0; k < 3; ++k) if (c->cfg.domain_max[k] > c->cfg.domain_min[k]) given = true;
     if (!given) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "multi-GPU runs need an explicit cell-grid domain (config.domain_min/max) shared by all ranks");
     if (!(slab_hi > slab_lo)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "empty slab");
+    if (axis < 0 || axis > 2) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "slab axis must be 0, 1 or 2");
+    c->slab_axis = axis;
     if (world == 1) return DFSPH_B200_OK;
     std::string err;
     if (!c->nccl.load(err)) CTX_FAIL(c, DFSPH_B200_ERR_COMM, "%s", err.c_str());

@@ -1,4 +1,4 @@
-// Multi-GPU slab decomposition along x (SURVEY.md row e): one context per GPU / process, ghost particles of one
+// Multi-GPU slab decomposition along one coordinate axis (SURVEY.md row e): one context per GPU / process, ghost particles of one
 // support radius appended behind the owned particles, refreshed over NCCL send/recv; particle migration each step;
 // the density-error sum and the CFL maximum are all-reduced so that every rank takes identical loop decisions.
 // NCCL is resolved at run time with dlopen (the process usually already holds torch's libnccl.so.2).
@@ -48,6 +48,9 @@ struct ExchangeCounts {
     unsigned exp_all, pad0, pad1, pad2;   // union of the two export sets (processed first by the solver passes)
 };
 
+// coordinate along the slab axis (0 = x, 1 = y, 2 = z)
+__device__ __forceinline__ double slab_coord(const Real4& p, int axis) { return (double)(axis == 0 ? p.x : (axis == 1 ? p.y : p.z)); }
+
 // ---- migration --------------------------------------------------------------------------------------------------
 struct MigrantAux { Real kappa, kappa_v; unsigned id, state; };
 
@@ -55,14 +58,14 @@ struct MigrantAux { Real kappa, kappa_v; unsigned id, state; };
 // owned set by the cell sort, which files them under the dump key `num_keys` (see k_cell_hash_slab).
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_pack_leavers(unsigned n, const Real4* __restrict__ pos, const Real4* __restrict__ vel,
     const Real* __restrict__ kappa, const Real* __restrict__ kappa_v, const unsigned* __restrict__ id, const unsigned* __restrict__ state,
-    double lo, double hi, int has_left, int has_right, unsigned cap,
+    double lo, double hi, int axis, int has_left, int has_right, unsigned cap,
     Real4* __restrict__ pl, Real4* __restrict__ vl, MigrantAux* __restrict__ al,
     Real4* __restrict__ pr, Real4* __restrict__ vr, MigrantAux* __restrict__ ar, ExchangeCounts* cnt)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Real4 p = pos[i];
-    const double x = (double)p.x;
+    const double x = slab_coord(p, axis);
     if (has_left && x < lo) {
         const unsigned k = atomicAdd(&cnt->leave_l, 1u);
         if (k < cap) { pl[k] = p; vl[k] = vel[i]; al[k] = MigrantAux{kappa[i], kappa_v[i], id[i], state[i]}; }
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_unpack_arrivals(unsigned count,
 }
 
 // cell hash with the slab filter: leavers get the dump key (sorted behind every real cell, then cut off)
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash_slab(const Real4* __restrict__ pos, unsigned n, GridDesc g, double lo, double hi,
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash_slab(const Real4* __restrict__ pos, unsigned n, GridDesc g, double lo, double hi, int axis,
     int has_left, int has_right, unsigned* __restrict__ cell_count, unsigned* __restrict__ key_out, unsigned* __restrict__ rank_out,
     unsigned* __restrict__ fine_out)
 {
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash_slab(const Real4* __r
     const int cy = cell_coord_fine(p.y, g.oy, g.inv_cell, g.ny, sy);
     const int cz = cell_coord_fine(p.z, g.oz, g.inv_cell, g.nz, sz);
     unsigned key = cell_key(cx, cy, cz, g);
-    const double x = (double)p.x;
+    const double x = slab_coord(p, axis);
     if ((has_left && x < lo) || (has_right && x >= hi)) key = g.num_keys;
     key_out[i] = key;
     fine_out[i] = spread3(sx) | (spread3(sy) << 1) | (spread3(sz) << 2);
@@ -103,13 +106,13 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash_slab(const Real4* __r
 
 // ---- ghost exports -------------------------------------------------------------------------------------------------
 // Owned (sorted) particles within `width` of a slab face are exported to that neighbour.
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_select_exports(unsigned n, const Real4* __restrict__ pos, double lo, double hi, double width,
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_select_exports(unsigned n, const Real4* __restrict__ pos, double lo, double hi, double width, int axis,
     int has_left, int has_right, unsigned cap, unsigned* __restrict__ exp_l, unsigned* __restrict__ exp_r,
     unsigned* __restrict__ exp_all, unsigned char* __restrict__ is_export, ExchangeCounts* cnt)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double x = (double)pos[i].x;
+    const double x = slab_coord(pos[i], axis);
     const bool l = has_left && x < lo + width, r = has_right && x >= hi - width;
     if (l) { const unsigned k = atomicAdd(&cnt->exp_l, 1u); if (k < cap) exp_l[k] = i; }
     if (r) { const unsigned k = atomicAdd(&cnt->exp_r, 1u); if (k < cap) exp_r[k] = i; }

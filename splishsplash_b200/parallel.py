@@ -31,15 +31,15 @@ def owner_of(x, bounds):
     return np.searchsorted(his, x, side="right")
 
 
-def select_slab(scene, rank: int, world: int, bounds=None, halo_cells: float = 2.0):
+def select_slab(scene, rank: int, world: int, bounds=None, halo_cells: float = 2.0, axis: int = 0):
     """Per-rank view of a global scene dict: owned fluid particles (with global ids), the boundary particles within
     `halo_cells` cells of the slab, the slab itself and the global cell-grid domain every rank must share."""
     x = np.asarray(scene["fluid_x"])
     bx = scene.get("boundary_x")
     if bounds is None:
-        bounds = slab_bounds(float(x[:, 0].min()), float(np.nextafter(x[:, 0].max(), np.inf)), world)
+        bounds = slab_bounds(float(x[:, axis].min()), float(np.nextafter(x[:, axis].max(), np.inf)), world)
     lo, hi = bounds[rank]
-    own = np.nonzero((x[:, 0].astype(np.float64) >= lo) & (x[:, 0].astype(np.float64) < hi))[0]
+    own = np.nonzero((x[:, axis].astype(np.float64) >= lo) & (x[:, axis].astype(np.float64) < hi))[0]
     cell = 4.0 * scene["radius"] * (1.0 + 1.0e-5)
     out = dict(scene)
     out["fluid_x"] = np.ascontiguousarray(x[own])
@@ -49,18 +49,19 @@ def select_slab(scene, rank: int, world: int, bounds=None, halo_cells: float = 2
     pts = [x.min(axis=0), x.max(axis=0)]
     if bx is not None and len(bx):
         b = np.asarray(bx)
-        keep = (b[:, 0].astype(np.float64) >= lo - halo_cells * cell) & (b[:, 0].astype(np.float64) < hi + halo_cells * cell)
+        keep = (b[:, axis].astype(np.float64) >= lo - halo_cells * cell) & (b[:, axis].astype(np.float64) < hi + halo_cells * cell)
         out["boundary_x"] = np.ascontiguousarray(b[keep])
         out["boundary_keep"] = np.nonzero(keep)[0]
         pts += [b.min(axis=0), b.max(axis=0)]
     pts = np.asarray(pts, dtype=np.float64)
     out["domain"] = (pts.min(axis=0) - cell, pts.max(axis=0) + cell)
     out["slab"] = (lo, hi)
+    out["slab_axis"] = axis
     out["bounds"] = bounds
     return out
 
 
-def bootstrap_comm(ts, rank: int, world: int, slab):
+def bootstrap_comm(ts, rank: int, world: int, slab, axis: int = 0):
     """Create the NCCL communicator of a TimeStepDFSPH_B200 context: rank 0 draws the unique id, torch.distributed
     broadcasts the 256 bytes, every rank calls dfsph_b200_comm_init.  Must run before set_fluid."""
     import torch.distributed as dist
@@ -71,7 +72,7 @@ def bootstrap_comm(ts, rank: int, world: int, slab):
     if world > 1:
         dist.broadcast_object_list(obj, src=0)
     idb = (C.c_char * 256).from_buffer_copy(obj[0])
-    ts._check(ts.lib.dfsph_b200_comm_init(ts.ctx, idb, rank, world, float(slab[0]), float(slab[1])))
+    ts._check(ts.lib.dfsph_b200_comm_init(ts.ctx, idb, rank, world, int(axis), float(slab[0]), float(slab[1])))
 
 
 def enable_p2p(ts, rank: int, world: int):
@@ -92,7 +93,7 @@ def build_b200_slab(scene_rank, precision, rank, world, kernel=4, device=0, boun
     ts = TimeStepDFSPH_B200(precision, scene_rank["radius"], kernel, device=device, domain=scene_rank["domain"])
     if params:
         ts.set(**params)
-    bootstrap_comm(ts, rank, world, scene_rank["slab"])
+    bootstrap_comm(ts, rank, world, scene_rank["slab"], scene_rank.get("slab_axis", 0))
     ts.set_fluid(scene_rank["fluid_x"], scene_rank.get("fluid_v"), ids=scene_rank["fluid_ids"])
     bx = scene_rank.get("boundary_x")
     if bx is not None and len(bx):

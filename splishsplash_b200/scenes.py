@@ -81,9 +81,20 @@ def fluid_block(box_min, box_max, radius, dtype=np.float32, dense_mode=0):
     return x.reshape(-1, 3)
 
 
-def box_boundary(box_min, box_max, radius, dtype=np.float32, spacing_factor=1.5, x_range=None):
+def box_boundary(box_min, box_max, radius, dtype=np.float32, spacing_factor=1.5, x_range=None, axis_range=None):
     """One layer of boundary particles on the six faces of an axis-aligned box, no duplicates on edges.
-    x_range = (a, b): only the particles with a <= x < b are generated (per-rank portion of a long tank)."""
+    x_range = (a, b) / axis_range = (axis, a, b): only the particles with a <= coordinate < b are generated (the per-rank
+    portion of a long tank)."""
+    if axis_range is not None and axis_range[0] != 0:
+        # permute so that the filtered axis becomes x, generate, permute back
+        ax_, a, b = axis_range
+        perm = [ax_] + [k for k in range(3) if k != ax_]
+        inv = np.argsort(perm)
+        pts = box_boundary(np.asarray(box_min, dtype=np.float64)[perm], np.asarray(box_max, dtype=np.float64)[perm], radius, dtype,
+                           spacing_factor, x_range=(a, b))
+        return np.ascontiguousarray(pts[:, inv])
+    if axis_range is not None:
+        x_range = (axis_range[1], axis_range[2])
     bmin = np.asarray(box_min, dtype=np.float64)
     bmax = np.asarray(box_max, dtype=np.float64)
     s = spacing_factor * float(radius)
@@ -150,40 +161,47 @@ def dam_break(counts="tiny", radius=0.025, dtype=np.float32, tank_x_factor=3.0, 
 
 
 def dam_break_weak(rank, world, counts="10M", radius=0.025, dtype=np.float32, tank_x_factor=3.0, tank_y_factor=1.5,
-                   spacing_factor=1.5, halo_cells=2.0):
-    """Weak-scaling scene: `world` blocks of the named size side by side along x in one long tank; rank
-    r generates ONLY its own block (global particle ids), its slab [lo, hi) and the boundary particles within
-    `halo_cells` cells of the slab.  The global scene is never materialised.  Returns the per-rank dict that
-    splishsplash_b200.parallel.build_b200_slab expects."""
+                   spacing_factor=1.5, halo_cells=2.0, axis=2):
+    """Weak-scaling scene: `world` blocks of the named size side by side along `axis` in one tank; rank
+    r generates ONLY its own block (global particle ids), its slab [lo, hi) along `axis` and the boundary particles
+    within `halo_cells` cells of the slab.  The global scene is never materialised.
+
+    axis = 2 (default): the dam is replicated across the tank (z), slabs are perpendicular to the flow, so every GPU
+    sees the same dam-break physics for the whole run (same iteration counts as the single-GPU block, no load drift).
+    axis = 0: blocks side by side along the flow direction (SURVEY.md 8d wording): one long block; the larger global
+    system needs more Jacobi iterations and the fluid drifts towards the last ranks as the dam collapses."""
     if isinstance(counts, str):
         counts = NAMED_BLOCKS[counts]
+    if axis not in (0, 2):
+        raise ValueError("axis 0 (x) or 2 (z)")
     nx, ny, nz = counts
     dt = np.dtype(dtype).type
     d = 2.0 * radius
-    gx = nx * world
-    block = np.array([(gx + 1) * d, (ny + 1) * d, (nz + 1) * d])
+    g = [nx, ny, nz]
+    g[axis] *= world
+    block = np.array([(g[0] + 1) * d, (g[1] + 1) * d, (g[2] + 1) * d])
     tmin = np.zeros(3)
     tmax = np.array([tank_x_factor * block[0], tank_y_factor * block[1], block[2]])
     # the same position arithmetic as fluid_lattice for the global lattice (index * diam + start, in Real)
     diam = dt(2.0) * dt(radius)
-    ix = np.arange(rank * nx, (rank + 1) * nx)
-    axx = (ix.astype(dtype) * diam + dt(d)).astype(dtype)
-    axy = (np.arange(ny, dtype=dtype) * diam + dt(d)).astype(dtype)
-    axz = (np.arange(nz, dtype=dtype) * diam + dt(d)).astype(dtype)
+    idx = [np.arange(nx), np.arange(ny), np.arange(nz)]
+    idx[axis] = np.arange(rank * counts[axis], (rank + 1) * counts[axis])
+    ax = [(i.astype(dtype) * diam + dt(d)).astype(dtype) for i in idx]
     x = np.empty((nx, ny, nz, 3), dtype=dtype)
-    x[..., 0] = axx[:, None, None]
-    x[..., 1] = axy[None, :, None]
-    x[..., 2] = axz[None, None, :]
-    ids = ((ix[:, None, None].astype(np.int64) * ny + np.arange(ny)[None, :, None]) * nz + np.arange(nz)[None, None, :])
+    x[..., 0] = ax[0][:, None, None]
+    x[..., 1] = ax[1][None, :, None]
+    x[..., 2] = ax[2][None, None, :]
+    ids = ((idx[0][:, None, None].astype(np.int64) * g[1] + idx[1][None, :, None]) * g[2] + idx[2][None, None, :])
     # slab faces half-way between lattice planes
-    face = lambda k: d + (k * nx - 0.5) * d
+    face = lambda k: d + (k * counts[axis] - 0.5) * d
     lo = -1.0e300 if rank == 0 else face(rank)
     hi = 1.0e300 if rank == world - 1 else face(rank + 1)
     cell = 4.0 * radius * (1.0 + 1.0e-5)
-    bnd = box_boundary(tmin, tmax, radius, dtype, spacing_factor, x_range=(lo - halo_cells * cell, hi + halo_cells * cell))
+    bnd = box_boundary(tmin, tmax, radius, dtype, spacing_factor, axis_range=(axis, lo - halo_cells * cell, hi + halo_cells * cell))
     return {"fluid_x": x.reshape(-1, 3), "fluid_ids": ids.reshape(-1).astype(np.uint32), "boundary_x": bnd,
-            "radius": float(radius), "counts": tuple(counts), "slab": (lo, hi), "domain": (tmin - cell, tmax + cell),
-            "tank_min": tmin, "tank_max": tmax, "global_particles": int(gx) * ny * nz}
+            "radius": float(radius), "counts": tuple(counts), "slab": (lo, hi), "slab_axis": axis,
+            "domain": (tmin - cell, tmax + cell), "tank_min": tmin, "tank_max": tmax,
+            "global_particles": int(g[0]) * g[1] * g[2], "global_counts": tuple(g)}
 
 
 def rw_state_scene(dtype=np.float32):

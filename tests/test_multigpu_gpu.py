@@ -17,11 +17,13 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_two_slabs_reproduce_single_gpu(prec):
+@pytest.mark.parametrize("prec,axis,p2p", [("f64", 0, "1"), ("f32", 2, "1"), ("f64", 2, "0")])
+def test_two_slabs_reproduce_single_gpu(prec, axis, p2p):
+    """p2p = "1": NVLink peer-memory refresh + fused all-reduce; "0": NCCL send/recv + ncclAllReduce."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tools", "multigpu_check.py"), prec, "small", "25"]
+           "--master-port", "29533", os.path.join(ROOT, "tools", "multigpu_check.py"), prec, "small", "25", str(axis)]
+    os.environ["DFSPH_B200_P2P"] = p2p
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

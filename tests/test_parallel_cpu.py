@@ -96,17 +96,19 @@ def test_slab_bounds_and_owner():
         assert np.array_equal(p["domain"][0], parts[0]["domain"][0])   # shared cell grid
 
 
-def test_weak_scaling_scene_tiles_the_global_block():
+@pytest.mark.parametrize("axis", [0, 2])
+def test_weak_scaling_scene_tiles_the_global_block(axis):
     world = 4
-    parts = [scenes.dam_break_weak(r, world, "tiny", dtype=np.float32) for r in range(world)]
+    parts = [scenes.dam_break_weak(r, world, "tiny", dtype=np.float32, axis=axis) for r in range(world)]
     ids = np.concatenate([p["fluid_ids"] for p in parts])
     assert len(np.unique(ids)) == len(ids) == parts[0]["global_particles"] == 4 * 1200
-    g = scenes.fluid_lattice((10 * world, 12, 10), 0.025, (0.05, 0.05, 0.05), np.float32)
+    g = scenes.fluid_lattice(parts[0]["global_counts"], 0.025, (0.05, 0.05, 0.05), np.float32)
     x = np.empty_like(g)
     for p in parts:
         x[p["fluid_ids"]] = p["fluid_x"]
         lo, hi = p["slab"]
-        assert ((p["fluid_x"][:, 0] >= lo) & (p["fluid_x"][:, 0] < hi)).all()
+        assert p["slab_axis"] == axis
+        assert ((p["fluid_x"][:, axis].astype(np.float64) >= lo) & (p["fluid_x"][:, axis].astype(np.float64) < hi)).all()
     assert np.array_equal(x, g)
     # slabs are contiguous and the per-rank boundary portions cover the whole tank boundary
     for a, b in zip(parts[:-1], parts[1:]):

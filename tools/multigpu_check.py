@@ -18,14 +18,15 @@ def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "f64"
     name = sys.argv[2] if len(sys.argv) > 2 else "small"
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    axis = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sc = scenes.dam_break(name, dtype=dtype_of(prec))
     # give the block an initial velocity towards +x so that particles migrate across the slab faces
-    v = np.zeros_like(sc["fluid_x"]); v[:, 0] = 0.8
+    v = np.zeros_like(sc["fluid_x"]); v[:, axis] = 0.8
     sc["fluid_v"] = v
-    mine = parallel.select_slab(sc, rank, world)
+    mine = parallel.select_slab(sc, rank, world, axis=axis)
     # boundary volumes must come from the global boundary (a per-rank subset would change V near the cut)
     single = build_b200_scene(sc, prec, device=local) if True else None
     bV = single.boundary_volume()
@@ -56,7 +57,7 @@ def main():
         tol = (1e-8 if prec == "f64" else 2e-3)   # free-running for `steps` steps: rounding differences accumulate
         same_iters = iters_m == iters_s
         ok = same_iters and all(e <= tol for e in worst.values())
-        print(f"[{prec} {name} world={world}] owned per rank {counts} steps={steps} iters equal={same_iters} "
+        print(f"[{prec} {name} world={world} axis={axis}] owned per rank {counts} steps={steps} iters equal={same_iters} "
               f"worst={max(worst.items(), key=lambda kv: kv[1])} ok={ok}")
         print("   ", {k: f"{e:.2e}" for k, e in worst.items()})
         if not same_iters:
