@@ -195,6 +195,7 @@ int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id256, int rank, int w
  * path is used. */
 int dfsph_b200_p2p_export(dfsph_b200_ctx* ctx, void* blob512);
 int dfsph_b200_p2p_import(dfsph_b200_ctx* ctx, const void* blobs_all /* world_size x 512 bytes, in rank order */);
+int dfsph_b200_p2p_disable(dfsph_b200_ctx* ctx);   /* all ranks together, between steps: back to the NCCL path */
 
 /* Device timing.  timer_start/stop bracket any number of calls with two CUDA events on the context's own stream
  * (the stream every kernel of this library is launched on).  With profiling on, every launch of the kernel classes

@@ -62,6 +62,7 @@ EXPORTS = [
     "dfsph_b200_eval_kernel", "dfsph_b200_alloc_pinned", "dfsph_b200_free_pinned", "dfsph_b200_synchronize",
     "dfsph_b200_set_profiling", "dfsph_b200_get_profile", "dfsph_b200_timer_start", "dfsph_b200_timer_stop",
     "dfsph_b200_comm_get_unique_id", "dfsph_b200_comm_init", "dfsph_b200_p2p_export", "dfsph_b200_p2p_import",
+    "dfsph_b200_p2p_disable",
 ]
 
 PROF_CLASSES = ["sort", "build_neighbors", "init_sweep", "accel", "jacobi_div", "jacobi_press", "div_final",
@@ -121,6 +122,7 @@ def load(precision: str = "f32"):
     L.dfsph_b200_comm_init.argtypes = [P, P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
     L.dfsph_b200_p2p_export.argtypes = [P, P]
     L.dfsph_b200_p2p_import.argtypes = [P, P]
+    L.dfsph_b200_p2p_disable.argtypes = [P]
     want = 4 if precision == "f32" else 8
     if L.dfsph_b200_sizeof_real() != want:
         raise RuntimeError(f"{path}: sizeof(Real) mismatch")

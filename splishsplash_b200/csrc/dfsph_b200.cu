@@ -1542,29 +1542,32 @@ int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128 /* the 256 bytes o
 }
 
 // P2P blob layout: 8 cudaIpcMemHandle_t (pos[0], pos[1], vel[0], vel[1], acc, flags, reduce values, reduce sequence words) = 512 bytes
+// like CUDA_TRY but not sticky: a failed peer mapping only means "stay on the NCCL path"
+#define CUDA_SOFT(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); \
+    CTX_FAIL(ctx, DFSPH_B200_ERR_COMM, "%s failed: %s", #expr, cudaGetErrorString(_e)); } } while (0)
 int dfsph_b200_p2p_export(dfsph_b200_ctx* c, void* blob512)
 {
     CHECK_CTX(c);
     cudaSetDevice(c->cfg.device);
     if (!blob512) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "null blob");
     if (!c->multi || c->cap == 0) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "call comm_init and set_fluid first");
-    if (!c->flags) { if (dev_alloc(c, &c->flags, 8)) return DFSPH_B200_ERR_CUDA; CUDA_TRY(c, cudaMemset(c->flags, 0, 8 * sizeof(unsigned))); }
+    if (!c->flags) { if (dev_alloc(c, &c->flags, 8)) return DFSPH_B200_ERR_CUDA; CUDA_SOFT(c, cudaMemset(c->flags, 0, 8 * sizeof(unsigned))); }
     memset(blob512, 0, 512);
     cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)blob512;
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[0], c->pos[0]));
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[1], c->pos[1]));
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[2], c->vel[0]));
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[3], c->vel[1]));
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[4], c->acc));
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[5], c->flags));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[0], c->pos[0]));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[1], c->pos[1]));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[2], c->vel[0]));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[3], c->vel[1]));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[4], c->acc));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[5], c->flags));
     if (!c->red_val) {
         if (dev_alloc(c, &c->red_val, 2 * DFSPH_MAX_RANKS)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->red_seq, DFSPH_MAX_RANKS)) return DFSPH_B200_ERR_CUDA;
-        CUDA_TRY(c, cudaMemset(c->red_val, 0, 2 * DFSPH_MAX_RANKS * sizeof(double)));
-        CUDA_TRY(c, cudaMemset(c->red_seq, 0, DFSPH_MAX_RANKS * sizeof(unsigned)));
+        CUDA_SOFT(c, cudaMemset(c->red_val, 0, 2 * DFSPH_MAX_RANKS * sizeof(double)));
+        CUDA_SOFT(c, cudaMemset(c->red_seq, 0, DFSPH_MAX_RANKS * sizeof(unsigned)));
     }
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[6], c->red_val));
-    CUDA_TRY(c, cudaIpcGetMemHandle(&h[7], c->red_seq));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[6], c->red_val));
+    CUDA_SOFT(c, cudaIpcGetMemHandle(&h[7], c->red_seq));
     return DFSPH_B200_OK;
 }
 
@@ -1583,8 +1586,8 @@ int dfsph_b200_p2p_import(dfsph_b200_ctx* c, const void* blobs_all)
         if (r == c->rank) { c->pr.val[r] = c->red_val; c->pr.seq[r] = c->red_seq; continue; }
         const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)(all + 512 * r);
         void *pv = nullptr, *ps = nullptr;
-        CUDA_TRY(c, cudaIpcOpenMemHandle(&pv, h[6], cudaIpcMemLazyEnablePeerAccess));
-        CUDA_TRY(c, cudaIpcOpenMemHandle(&ps, h[7], cudaIpcMemLazyEnablePeerAccess));
+        CUDA_SOFT(c, cudaIpcOpenMemHandle(&pv, h[6], cudaIpcMemLazyEnablePeerAccess));
+        CUDA_SOFT(c, cudaIpcOpenMemHandle(&ps, h[7], cudaIpcMemLazyEnablePeerAccess));
         c->red_opened.push_back(pv); c->red_opened.push_back(ps);
         c->pr.val[r] = (double*)pv; c->pr.seq[r] = (unsigned*)ps;
     }
@@ -1595,13 +1598,20 @@ int dfsph_b200_p2p_import(dfsph_b200_ctx* c, const void* blobs_all)
         if (!blobs[s]) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "missing neighbour blob");
         const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)blobs[s];
         void* p[6];
-        for (int k = 0; k < 6; ++k) CUDA_TRY(c, cudaIpcOpenMemHandle(&p[k], h[k], cudaIpcMemLazyEnablePeerAccess));
+        for (int k = 0; k < 6; ++k) CUDA_SOFT(c, cudaIpcOpenMemHandle(&p[k], h[k], cudaIpcMemLazyEnablePeerAccess));
         c->peer[s].pos[0] = (Real4*)p[0]; c->peer[s].pos[1] = (Real4*)p[1];
         c->peer[s].vel[0] = (Real4*)p[2]; c->peer[s].vel[1] = (Real4*)p[3];
         c->peer[s].acc = (Real4*)p[4]; c->peer[s].flags = (unsigned*)p[5];
         c->peer[s].open = true;
     }
     c->p2p = true;
+    return DFSPH_B200_OK;
+}
+
+int dfsph_b200_p2p_disable(dfsph_b200_ctx* c)
+{
+    CHECK_CTX(c);
+    c->p2p = false;     // back to NCCL send/recv + ncclAllReduce (all ranks must switch together, between steps)
     return DFSPH_B200_OK;
 }
 

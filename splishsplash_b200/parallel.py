@@ -80,11 +80,22 @@ def enable_p2p(ts, rank: int, world: int):
     every rank its neighbours'.  Must run after set_fluid (the buffers must exist)."""
     import torch.distributed as dist
     blob = (C.c_char * 512)()
-    ts._check(ts.lib.dfsph_b200_p2p_export(ts.ctx, blob))
+    ok = ts.lib.dfsph_b200_p2p_export(ts.ctx, blob) == 0
     blobs = [None] * world
-    dist.all_gather_object(blobs, bytes(blob.raw))
-    allb = (C.c_char * (512 * world)).from_buffer_copy(b"".join(blobs))
-    ts._check(ts.lib.dfsph_b200_p2p_import(ts.ctx, allb))
+    dist.all_gather_object(blobs, (ok, bytes(blob.raw)))
+    if all(b[0] for b in blobs):
+        allb = (C.c_char * (512 * world)).from_buffer_copy(b"".join(b[1] for b in blobs))
+        ok = ts.lib.dfsph_b200_p2p_import(ts.ctx, allb) == 0
+    else:
+        ok = False
+    # every rank must end up on the same path: if peer mapping failed anywhere (no NVLink peer access, IPC disabled in
+    # the container, more than 16 ranks) all ranks stay on NCCL send/recv + ncclAllReduce
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if not all(oks):
+        ts.lib.dfsph_b200_p2p_disable(ts.ctx)
+        return False
+    return True
 
 
 def build_b200_slab(scene_rank, precision, rank, world, kernel=4, device=0, boundary_V=None, p2p=None, **params):
