@@ -88,6 +88,11 @@ typedef struct {
     double cfl_factor;              /* 0.5 */
     double cfl_min_time_step_size;  /* 1e-4 */
     double cfl_max_time_step_size;  /* 5e-3 */
+    /* next-row f1: FluidModel "viscosityMethod" (0 none, 1 "Standard viscosity") and the Viscosity_Standard
+     * parameters "viscosity" / "viscosityBoundary" (Viscosity/Viscosity_Standard.cpp:21-22,33-44).  Other methods: */
+    int32_t viscosity_method;       /* default here 0; the reference's FluidModel default is 1 (FluidModel.cpp:98) */
+    double viscosity;               /* 0.01 */
+    double viscosity_boundary;      /* 0.0 */
 } dfsph_b200_params;
 
 typedef struct {

@@ -50,6 +50,9 @@ struct Sim {
     unsigned minIter = 2, maxIter = 100, maxIterV = 100;
     Real maxError = static_cast<Real>(0.01), maxErrorV = static_cast<Real>(0.1);
     bool enableDiv = true;
+    int viscosityMethod = 0;       // 0 none, 1 Viscosity_Standard
+    Real viscosity = static_cast<Real>(0.01), viscosityBoundary = 0;
+    std::vector<V3> acc;           // non-pressure accelerations (FluidModel::m_a)
     unsigned iterations = 0, iterationsV = 0;
     // kernel constants
     Real k = 0, l = 0, W_zero = 0, invR = 0, invR2 = 0, lutInvStep = 0;
@@ -494,14 +497,45 @@ void pressureSolve()
     }
 }
 
-// Simulation::updateTimeStepSize (Simulation.cpp:395-493); accelerations are the gravity vector (TimeStep.cpp:35-50)
+// TimeStep::clearAccelerations (TimeStep.cpp:35-50) + Viscosity_Standard::step (Viscosity/Viscosity_Standard.cpp:48-238 /
+// 242-400): a_i = g + 10 mu sum_j (m_j/rho_j) (v_ij.x_ij)/(|x_ij|^2 + 0.01 h^2) gradW_ij (+ boundary term)
+void computeNonPressureForces()
+{
+    const long n = (long)g->x.size();
+    g->acc.resize(n);
+    const Real h2 = g->support * g->support;
+    #pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        V3 a = { g->gravity[0], g->gravity[1], g->gravity[2] };
+        if (g->viscosityMethod == 1) {
+            const V3 xi = g->x[i], vi = g->v[i];
+            FOR_FLUID(i, j)
+                const V3 xixj = xi - g->x[j];
+                const V3 w = solverGradW(xixj);
+                const Real s = static_cast<Real>(10.0) * g->viscosity * (g->V * g->density0 / g->density[j]) * dot(vi - g->v[j], xixj) / (dot(xixj, xixj) + static_cast<Real>(0.01) * h2);
+                a = { a.x + s * w.x, a.y + s * w.y, a.z + s * w.z };
+            END_FOR
+            if (g->viscosityBoundary != 0.0) {
+                FOR_BOUNDARY(i, j)
+                    const V3 xixj = xi - g->bx[j];
+                    const V3 w = solverGradW(xixj);
+                    const Real s = static_cast<Real>(10.0) * g->viscosityBoundary * (g->density0 * g->bV[j] / g->density[i]) * dot(vi, xixj) / (dot(xixj, xixj) + static_cast<Real>(0.01) * h2);
+                    a = { a.x + s * w.x, a.y + s * w.y, a.z + s * w.z };
+                END_FOR
+            }
+        }
+        g->acc[i] = a;
+    }
+}
+
+// Simulation::updateTimeStepSize (Simulation.cpp:395-493)
 void updateTimeStepSize()
 {
     if (g->cflMethod != 1 && g->cflMethod != 2) return;
     const Real hOld = g->h;
     Real maxVel = 0.0;
     for (size_t i = 0; i < g->x.size(); ++i) {
-        const V3 t = { g->v[i].x + g->gravity[0] * hOld, g->v[i].y + g->gravity[1] * hOld, g->v[i].z + g->gravity[2] * hOld };
+        const V3 t = { g->v[i].x + g->acc[i].x * hOld, g->v[i].y + g->acc[i].y * hOld, g->v[i].z + g->acc[i].z * hOld };
         const Real m = dot(t, t);
         if (m > maxVel) maxVel = m;
     }
@@ -528,10 +562,11 @@ void step()
     computeDensities();
     computeFactor();
     if (g->enableDiv) divergenceSolve(); else g->iterationsV = 0;
+    computeNonPressureForces();
     updateTimeStepSize();
     #pragma omp parallel for schedule(static)
     for (long i = 0; i < n; ++i)
-        g->v[i] = { g->v[i].x + h * g->gravity[0], g->v[i].y + h * g->gravity[1], g->v[i].z + h * g->gravity[2] };
+        g->v[i] = { g->v[i].x + h * g->acc[i].x, g->v[i].y + h * g->acc[i].y, g->v[i].z + h * g->acc[i].z };
     pressureSolve();
     #pragma omp parallel for schedule(static)
     for (long i = 0; i < n; ++i)
@@ -611,6 +646,15 @@ int ref_set_int(const char* name, int v)
     return 0;
 }
 
+int ref_set_viscosity(int, int method, double viscosity, double viscosityBoundary)
+{
+    if (method != 0 && method != 1) return -1;
+    g->viscosityMethod = method;
+    g->viscosity = static_cast<Real>(viscosity);
+    g->viscosityBoundary = static_cast<Real>(viscosityBoundary);
+    return 0;
+}
+
 int ref_set_gravity(double gx, double gy, double gz)
 {
     g->gravity[0] = static_cast<Real>(gx); g->gravity[1] = static_cast<Real>(gy); g->gravity[2] = static_cast<Real>(gz);
@@ -650,7 +694,7 @@ int ref_get_field(int, const char* name, Real* out, int dim)
     if (s == "position") v3 = &g->x; else if (s == "velocity") v3 = &g->v; else if (s == "pressure acceleration") v3 = &g->pa;
     else if (s == "density") v1 = &g->density; else if (s == "factor") v1 = &g->factor; else if (s == "advected density") v1 = &g->density_adv;
     else if (s == "p / rho^2") v1 = &g->kappa; else if (s == "p_v / rho^2") v1 = &g->kappa_v;
-    else if (s == "acceleration") { for (size_t i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) out[3 * i + k] = g->gravity[k]; return 0; }
+    else if (s == "acceleration") { for (size_t i = 0; i < n; ++i) { const V3 a = i < g->acc.size() ? g->acc[i] : V3{ g->gravity[0], g->gravity[1], g->gravity[2] }; out[3 * i] = a.x; out[3 * i + 1] = a.y; out[3 * i + 2] = a.z; } return 0; }
     else return -1;
     if (v3) for (size_t i = 0; i < n; ++i) { out[3 * i] = (*v3)[i].x; out[3 * i + 1] = (*v3)[i].y; out[3 * i + 2] = (*v3)[i].z; }
     if (v1) for (size_t i = 0; i < n; ++i) out[i] = (*v1)[i];

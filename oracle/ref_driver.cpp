@@ -14,6 +14,7 @@
 #include "SPlisHSPlasH/BoundaryModel_Akinci2012.h"
 #include "SPlisHSPlasH/StaticRigidBody.h"
 #include "SPlisHSPlasH/DFSPH/TimeStepDFSPH.h"
+#include "SPlisHSPlasH/Viscosity/Viscosity_Standard.h"
 #include "TimeStepDFSPH_B200.h"   // the product's drop-in solver (splishsplash_b200/host), exercised through the reference stack
 #include "Utilities/Timing.h"
 #include "Utilities/Counting.h"
@@ -173,6 +174,20 @@ int ref_set_int(const char* name, int v)
 	else if (s == "enableZSort") sim->setValue<bool>(Simulation::ENABLE_Z_SORT, v != 0);
 	else if (s == "stepsPerZSort") sim->setValue<unsigned int>(Simulation::STEPS_PER_Z_SORT, (unsigned int)v);
 	else return -1;
+	return 0;
+}
+
+/* FluidModel "viscosityMethod" (0 none, 1 "Standard viscosity") + Viscosity_Standard parameters. */
+int ref_set_viscosity(int fluid, int method, double viscosity, double viscosityBoundary)
+{
+	FluidModel* fm = Simulation::getCurrent()->getFluidModel(fluid);
+	fm->setViscosityMethod((unsigned int)method);
+	if (method == 1)
+	{
+		NonPressureForceBase* v = fm->getViscosityBase();
+		v->setValue<Real>(Viscosity_Standard::VISCOSITY_COEFFICIENT, static_cast<Real>(viscosity));
+		v->setValue<Real>(Viscosity_Standard::VISCOSITY_COEFFICIENT_BOUNDARY, static_cast<Real>(viscosityBoundary));
+	}
 	return 0;
 }
 

@@ -62,6 +62,7 @@ class RefSim:
         L.ref_neighbor_counts.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.ref_neighbor_lists.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_set_num_threads.argtypes = [C.c_int]
+        L.ref_set_viscosity.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
         if hasattr(L, "ref_configure_b200"):   # only the reference build carries the drop-in solver
             L.ref_configure_b200.argtypes = [C.c_int, C.c_int, C.c_char_p]
             L.ref_last_error.restype = C.c_char_p
@@ -109,7 +110,14 @@ class RefSim:
     def finalize(self):
         self.lib.ref_finalize()
 
+    def set_viscosity(self, method=1, viscosity=0.01, viscosity_boundary=0.0, fluid=0):
+        if self.lib.ref_set_viscosity(fluid, int(method), float(viscosity), float(viscosity_boundary)) != 0:
+            raise ValueError("unsupported viscosity method")
+
     def set(self, **kw):
+        visc = {k: kw.pop(k) for k in ("viscosityMethod", "viscosity", "viscosityBoundary") if k in kw}
+        if visc:
+            self.set_viscosity(visc.get("viscosityMethod", 1), visc.get("viscosity", 0.01), visc.get("viscosityBoundary", 0.0))
         for k, v in kw.items():
             if k == "gravitation":
                 self.lib.ref_set_gravity(*[float(c) for c in v])

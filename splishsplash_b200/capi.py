@@ -42,7 +42,8 @@ class Params(C.Structure):
                 ("min_iterations", C.c_uint32), ("max_iterations", C.c_uint32), ("max_error", C.c_double),
                 ("max_iterations_v", C.c_uint32), ("max_error_v", C.c_double),
                 ("enable_divergence_solver", C.c_int32), ("cfl_method", C.c_int32), ("cfl_factor", C.c_double),
-                ("cfl_min_time_step_size", C.c_double), ("cfl_max_time_step_size", C.c_double)]
+                ("cfl_min_time_step_size", C.c_double), ("cfl_max_time_step_size", C.c_double),
+                ("viscosity_method", C.c_int32), ("viscosity", C.c_double), ("viscosity_boundary", C.c_double)]
 
 
 class StepStats(C.Structure):

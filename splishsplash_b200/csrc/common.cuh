@@ -156,6 +156,8 @@ struct SolverParams {
     int cfl_method;
     Real cfl_factor, cfl_min, cfl_max;
     Real radius;                      // particle radius
+    int viscosity_method;             // 0 none, 1 Viscosity_Standard
+    Real viscosity, viscosity_boundary;
 };
 
 #define DFSPH_BLOCK 256

@@ -264,6 +264,8 @@ static SolverParams make_solver_params(const dfsph_b200_ctx* c)
     sp.cfl_method = c->par.cfl_method;
     sp.cfl_factor = (Real)c->par.cfl_factor; sp.cfl_min = (Real)c->par.cfl_min_time_step_size; sp.cfl_max = (Real)c->par.cfl_max_time_step_size;
     sp.radius = (Real)c->cfg.particle_radius;
+    sp.viscosity_method = c->par.viscosity_method;
+    sp.viscosity = (Real)c->par.viscosity; sp.viscosity_boundary = (Real)c->par.viscosity_boundary;
     return sp;
 }
 
@@ -299,6 +301,9 @@ void dfsph_b200_default_params(dfsph_b200_params* p)
     p->cfl_factor = 0.5;
     p->cfl_min_time_step_size = 0.0001;
     p->cfl_max_time_step_size = 0.005;
+    p->viscosity_method = 0;            // the reference's FluidModel default is 1 (Standard, FluidModel.cpp:98); explicit here
+    p->viscosity = 0.01;                // Viscosity_Standard.cpp:21
+    p->viscosity_boundary = 0.0;
 }
 
 const char* dfsph_b200_last_error(const dfsph_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -768,6 +773,9 @@ int dfsph_b200_set_params(dfsph_b200_ctx* c, const dfsph_b200_params* p)
     if (q.max_error_v < 1e-6) q.max_error_v = 1e-6;
     if (!(q.time_step_size > 0.0)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "time_step_size must be > 0");
     if (q.cfl_method < 0 || q.cfl_method > 2) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "cfl_method must be 0, 1 or 2");
+    if (q.viscosity_method != 0 && q.viscosity_method != 1) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "viscosity_method: only 0 (none) and 1 (Standard viscosity) run on the B200 path");
+    if (q.viscosity < 0.0) q.viscosity = 0.0;
+    if (q.viscosity_boundary < 0.0) q.viscosity_boundary = 0.0;
     const bool h_changed = (q.time_step_size != c->par.time_step_size);
     c->par = q;
     if (h_changed && c->ctrl) {
@@ -1147,15 +1155,27 @@ static int run_solver(dfsph_b200_ctx* c)
         return 0;
     };
 
+    const bool visc = c->par.viscosity_method == 1;
     if (div) {
         // the reference's iteration is a no-op for an empty model: avg stays 0, one iteration is counted
         int rc = solve_loop(SOLVE_DIV, c->par.max_iterations_v, c->pred_iter_v);
         if (rc) return rc;
         ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
-        k_div_final<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
-    } else {
+        if (visc) k_div_final<MODE, true, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
+        else k_div_final<MODE, true, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
+    } else if (!visc) {
         ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
-        k_div_final<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
+        k_div_final<MODE, false, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
+    }
+    if (visc) {
+        // Simulation::computeNonPressureForces -> Viscosity_Standard::step (next-row f1), fused with clearAccelerations,
+        // the CFL scan and the kick; needs the post-divergence-solve velocities of the neighbours
+        if (multi) { int rg = exchange_ghosts(c, c->vel[c->cur]); if (rg) return rg; }   // ghost (v, rho)
+        Real4* vtmp = c->vel[1 - c->cur];
+        { ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
+          k_viscosity_kick<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->bpos, vtmp); }
+        if (n > 0) k_copy_real4<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(vtmp, c->vel[c->cur], n);
+        c->launches += 2;
     }
     if (multi) {
         NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->maxvel_bits, &c->ctrl->maxvel_bits, 1, ncclUint64, ncclMax, c->comm, st));   // CFL maximum

@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphCo
     // density (TimeStep.cpp:70,110 / 133,166)
     const Real density = (V * c.W_zero + (ff.dens + fb.dens)) * c.density0;
     f.density[i] = density;
+    f.vel[i].w = density;   // (v, rho) in one record: the viscosity sweep gathers both with one load
     st_real4(f.bgrad + i, make_real4(fb.bx, fb.by, fb.bz, (Real)0.0));
 
     // factor (TimeStepDFSPH.cpp:812-821 / 1170-1182)
@@ -455,7 +456,8 @@ __global__ void k_solve_begin(Ctrl* ctrl, int solve)
 }
 
 // ---- divergence finaliser + non-pressure kick + CFL -----------------------------------------------------------------
-template <int MODE, bool DIV_SOLVER>
+// KICK = false: only the divergence finaliser; the non-pressure kick and the CFL scan happen in k_viscosity_kick.
+template <int MODE, bool DIV_SOLVER, bool KICK>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_div_final(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -474,13 +476,109 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_div_final(FluidArrays f, SphCon
             f.factor[i] *= h;                                            // :518
             f.kappa_v[i] = xi.w * h;                                     // :536
         }
-        // clearAccelerations: a = g (TimeStep.cpp:41-48); CFL term |v + a h|^2 (Simulation.cpp:431-439)
-        const Real tx = v.x + sp.gx * h, ty = v.y + sp.gy * h, tz = v.z + sp.gz * h;
-        velmag = tx * tx + ty * ty + tz * tz;
-        if (st == 0u) { v.x += h * sp.gx; v.y += h * sp.gy; v.z += h * sp.gz; }   // TimeStepDFSPH.cpp:192-208
+        if (KICK) {
+            // clearAccelerations: a = g (TimeStep.cpp:41-48); CFL term |v + a h|^2 (Simulation.cpp:431-439)
+            const Real tx = v.x + sp.gx * h, ty = v.y + sp.gy * h, tz = v.z + sp.gz * h;
+            velmag = tx * tx + ty * ty + tz * tz;
+            if (st == 0u) { v.x += h * sp.gx; v.y += h * sp.gy; v.z += h * sp.gz; }   // TimeStepDFSPH.cpp:192-208
+        }
         st_real4(f.vel + i, v);
     }
-    // block max -> global max (non-negative floats order like their bit patterns)
+    if (KICK) {
+        // block max -> global max (non-negative floats order like their bit patterns)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) velmag = real_max(velmag, __shfl_xor_sync(0xffffffffu, velmag, d));
+        __shared__ Real wm[DFSPH_BLOCK / 32];
+        if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = velmag;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Real m = wm[0];
+            for (int w = 1; w < DFSPH_BLOCK / 32; ++w) m = real_max(m, wm[w]);
+#if DFSPH_REAL_IS_DOUBLE
+            atomicMax(&ctrl->maxvel_bits, (unsigned long long)__double_as_longlong(m));
+#else
+            atomicMax(&ctrl->maxvel_bits, (unsigned long long)__float_as_uint(m));
+#endif
+        }
+    }
+}
+
+// ---- Viscosity_Standard (next-row f1; Viscosity/Viscosity_Standard.cpp:48-238 AVX, :242-400 scalar) + kick + CFL -----------
+// a_i = g + d mu sum_j (m_j/rho_j) (v_ij . x_ij)/(|x_ij|^2 + 0.01 h^2) gradW_ij  [+ boundary term if mu_b != 0], d = 10;
+// then the CFL term and v += h a exactly as in k_div_final.  Neighbours read the pre-kick velocities, so the kicked
+// velocity goes to vel_out.
+template <int MODE>
+struct ViscosityF {
+    struct Data { Real4 x, v; Real rx, ry, rz, g; };
+    const Real4* pos; const Real4* vel; const SphConst& c;
+    Real4 xi, vi;
+    Real ax, ay, az, eps2, dvisc;
+    __device__ __forceinline__ ViscosityF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_, Real dvisc_)
+        : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), ax(0), ay(0), az(0), eps2((Real)0.01 * c_.R * c_.R), dvisc(dvisc_) {}
+    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(pos + j); d.v = ld_gather(vel + j); return d; }
+    __device__ __forceinline__ void prep(Data& d) const
+    {
+        d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+        d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+    }
+    __device__ __forceinline__ void apply(const Data& d)
+    {
+        const Real r2 = d.rx * d.rx + d.ry * d.ry + d.rz * d.rz;
+        const Real vx = (vi.x - d.v.x) * d.rx + (vi.y - d.v.y) * d.ry + (vi.z - d.v.z) * d.rz;
+        // d.v.w = rho_j (1 for the sentinel: its gradient is 0 anyway); dvisc = d * mu * V * rho0 = d * mu * m_j
+        const Real rho_j = d.v.w > (Real)0.0 ? d.v.w : (Real)1.0;
+        const Real s = d.g * ((dvisc / rho_j) * vx / (r2 + eps2));
+        ax += s * d.rx; ay += s * d.ry; az += s * d.rz;
+    }
+};
+
+template <int MODE>
+struct ViscosityBoundaryF {
+    struct Data { Real4 x; Real rx, ry, rz, g; };
+    const Real4* bpos; const SphConst& c;
+    Real4 xi, vi;
+    Real ax, ay, az, eps2, coef;
+    __device__ __forceinline__ ViscosityBoundaryF(const Real4* bpos_, const SphConst& c_, Real4 xi_, Real4 vi_, Real coef_)
+        : bpos(bpos_), c(c_), xi(xi_), vi(vi_), ax(0), ay(0), az(0), eps2((Real)0.01 * c_.R * c_.R), coef(coef_) {}
+    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(bpos + j); return d; }
+    __device__ __forceinline__ void prep(Data& d) const
+    {
+        d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+        d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+    }
+    __device__ __forceinline__ void apply(const Data& d)   // static boundary: v_b = 0; d.x.w = V_b
+    {
+        const Real r2 = d.rx * d.rx + d.ry * d.ry + d.rz * d.rz;
+        const Real vx = vi.x * d.rx + vi.y * d.ry + vi.z * d.rz;
+        const Real s = d.g * (coef * d.x.w * vx / (r2 + eps2));
+        ax += s * d.rx; ay += s * d.ry; az += s * d.rz;
+    }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_viscosity_kick(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl,
+                                                                  const Real4* __restrict__ bpos, Real4* __restrict__ vel_out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const Real h = ctrl->h;
+    Real velmag = (Real)0.0;
+    if (i < f.n) {
+        const Real4 xi = ld_gather(f.pos + i);
+        Real4 v = ld_gather(f.vel + i);
+        const unsigned st = f.state[i];
+        ViscosityF<MODE> fv(f, c, xi, v, (Real)10.0 * sp.viscosity * c.V * c.density0);
+        neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fv);
+        Real ax = sp.gx + fv.ax, ay = sp.gy + fv.ay, az = sp.gz + fv.az;
+        if (sp.viscosity_boundary != (Real)0.0) {
+            ViscosityBoundaryF<MODE> fb(bpos, c, xi, v, (Real)10.0 * sp.viscosity_boundary * c.density0 / f.density[i]);
+            neighbor_sweep<DFSPH_U1>(tab_ptr(f.tab_b, f.Kb, i), f.tcnt_b[i >> 5], fb);
+            ax += fb.ax; ay += fb.ay; az += fb.az;
+        }
+        const Real tx = v.x + ax * h, ty = v.y + ay * h, tz = v.z + az * h;     // Simulation.cpp:431-439
+        velmag = tx * tx + ty * ty + tz * tz;
+        if (st == 0u) { v.x += h * ax; v.y += h * ay; v.z += h * az; }           // TimeStepDFSPH.cpp:192-208
+        st_real4(vel_out + i, v);
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) velmag = real_max(velmag, __shfl_xor_sync(0xffffffffu, velmag, d));
     __shared__ Real wm[DFSPH_BLOCK / 32];

@@ -2,6 +2,7 @@
 #include "dfsph_b200.h"
 #include "SPlisHSPlasH/TimeManager.h"
 #include "SPlisHSPlasH/BoundaryModel_Akinci2012.h"
+#include "SPlisHSPlasH/Viscosity/Viscosity_Standard.h"
 #include "Utilities/Timing.h"
 #include "Utilities/Counting.h"
 #include "Utilities/Logger.h"
@@ -211,6 +212,15 @@ void TimeStepDFSPH_B200::pushParameters()
 	p.cfl_factor = sim->getValue<Real>(Simulation::CFL_FACTOR);
 	p.cfl_min_time_step_size = sim->getValue<Real>(Simulation::CFL_MIN_TIMESTEPSIZE);
 	p.cfl_max_time_step_size = sim->getValue<Real>(Simulation::CFL_MAX_TIMESTEPSIZE);
+	// FluidModel "viscosityMethod": 0 = none, 1 = "Standard viscosity" runs on the device (next-row f1)
+	FluidModel* fm = sim->getFluidModel(0);
+	p.viscosity_method = (int)fm->getViscosityMethod();
+	if (p.viscosity_method == 1)
+	{
+		NonPressureForceBase* v = fm->getViscosityBase();
+		p.viscosity = v->getValue<Real>(Viscosity_Standard::VISCOSITY_COEFFICIENT);
+		p.viscosity_boundary = v->getValue<Real>(Viscosity_Standard::VISCOSITY_COEFFICIENT_BOUNDARY);
+	}
 	check(m_api->set_params(m_ctx, &p), "dfsph_b200_set_params");
 }
 
@@ -220,10 +230,10 @@ void TimeStepDFSPH_B200::uploadModel()
 	if (sim->getBoundaryHandlingMethod() != BoundaryHandlingMethods::Akinci2012 && sim->numberOfBoundaryModels() > 0)
 		throw std::runtime_error("TimeStepDFSPH_B200: only boundaryHandlingMethod 0 (Akinci2012) is supported on the B200 path");
 	FluidModel* fm = sim->getFluidModel(0);
-	if (fm->getViscosityMethod() != 0 || fm->getVorticityMethod() != 0 || fm->getDragMethod() != 0 ||
+	if (fm->getViscosityMethod() > 1 || fm->getVorticityMethod() != 0 || fm->getDragMethod() != 0 ||
 		fm->getSurfaceTensionMethod() != 0 || fm->getElasticityMethod() != 0)
-		throw std::runtime_error("TimeStepDFSPH_B200: non-pressure forces run on the host in the reference; set viscosityMethod/"
-			"vorticityMethod/dragMethod/surfaceTensionMethod/elasticityMethod to 0 for the B200 path (SURVEY.md H6)");
+		throw std::runtime_error("TimeStepDFSPH_B200: of the non-pressure forces only viscosityMethod 0 (none) and 1 (Standard viscosity) "
+			"run on the B200 path; set vorticityMethod/dragMethod/surfaceTensionMethod/elasticityMethod to 0 (SURVEY.md H6)");
 
 	if (m_ctx) { m_api->destroy(m_ctx); m_ctx = nullptr; }
 	dfsph_b200_config cfg;

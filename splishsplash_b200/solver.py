@@ -24,6 +24,8 @@ _TS_PARAMS = {  # reference parameter name -> Params field
     # Simulation / TimeManager
     "timeStepSize": "time_step_size", "cflMethod": "cfl_method", "cflFactor": "cfl_factor",
     "cflMinTimeStepSize": "cfl_min_time_step_size", "cflMaxTimeStepSize": "cfl_max_time_step_size",
+    # FluidModel / Viscosity_Standard (next-row f1)
+    "viscosityMethod": "viscosity_method", "viscosity": "viscosity", "viscosityBoundary": "viscosity_boundary",
 }
 
 

@@ -26,7 +26,18 @@ FIXTURES = [  # name, scene factory, precision, kernel, steps, params
     ("dambreak_tiny_f64_k0", lambda dt: scenes.dam_break("tiny", dtype=dt), "f64", 0, 3, {}),
     ("rwstate_f64_k4", lambda dt: scenes.rw_state_scene(dtype=dt), "f64", 4, 2,
      dict(timeStepSize=0.005, cflFactor=1.0, maxError=0.05)),   # data/Scenes/ReadWriteStateTest.json settings
+    ("dambreak_tiny_visc_f64_k4", lambda dt: _sheared(scenes.dam_break("tiny", dtype=dt)), "f64", 4, 3,
+     dict(viscosityMethod=1, viscosity=0.05, viscosityBoundary=0.02)),   # next-row f1: Viscosity_Standard
+    ("dambreak_tiny_visc_f32_k4", lambda dt: _sheared(scenes.dam_break("tiny", dtype=dt)), "f32", 4, 3,
+     dict(viscosityMethod=1, viscosity=0.05, viscosityBoundary=0.0)),
 ]
+
+
+def _sheared(sc):
+    v = np.zeros_like(sc["fluid_x"])
+    v[:, 0] = 1.5 * np.sin(6.0 * sc["fluid_x"][:, 1])
+    sc["fluid_v"] = v
+    return sc
 
 
 def main():
@@ -35,6 +46,7 @@ def main():
         sc = factory(dt)
         sim = refsim.build_ref_scene(sc, prec, kernel=kernel, **params)
         out = {"fluid_x": sc["fluid_x"], "boundary_x": sc["boundary_x"], "radius": np.float64(sc["radius"]),
+               **({"fluid_v": sc["fluid_v"]} if sc.get("fluid_v") is not None else {}),
                "kernel": np.int32(kernel), "steps": np.int32(steps)}
         for k, v in params.items():
             out["param_" + k] = np.float64(v)

@@ -19,7 +19,10 @@ GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
 
 
 def _scene_from(g):
-    return {"fluid_x": g["fluid_x"], "boundary_x": g["boundary_x"], "radius": float(g["radius"])}
+    sc = {"fluid_x": g["fluid_x"], "boundary_x": g["boundary_x"], "radius": float(g["radius"])}
+    if "fluid_v" in g.files:
+        sc["fluid_v"] = g["fluid_v"]
+    return sc
 
 
 def _params_from(g):

