@@ -330,6 +330,41 @@ int ref_neighbor_lists(int fluid, int pid, const unsigned long long* offsets, un
 	return 0;
 }
 
+/* Neighbour counts through the drop-in's CompactNSearch-style facade (NeighborhoodSearch_B200) for point set `pid`
+   (0 fluid, 1.. boundary models), host index order.  Only valid after ref_configure_b200. */
+int ref_b200_neighbor_counts(int pid, unsigned int* counts, unsigned long long* checksum)
+{
+	if (!g_b200) return -1;
+	Simulation* sim = Simulation::getCurrent();
+	TimeStepDFSPH_B200* ts = static_cast<TimeStepDFSPH_B200*>(sim->getTimeStep());
+	try {
+		NeighborhoodSearch_B200 ns(*ts);
+		ns.find_neighbors();
+		const unsigned int n = sim->getFluidModel(0)->numActiveParticles();
+		unsigned long long cs = 0;
+		for (unsigned int i = 0; i < n; i++)
+		{
+			counts[i] = ns.n_neighbors((unsigned int)pid, i);
+			for (unsigned int k = 0; k < counts[i]; k++) cs += (unsigned long long)(i + 1) * (ns.neighbor((unsigned int)pid, i, k) + 7u);
+		}
+		*checksum = cs;
+	} catch (const std::exception& e) { g_err = e.what(); return -2; }
+	return 0;
+}
+
+/* the same checksum over the reference's own lists (array order = host order while no z-sort happened) */
+int ref_neighbor_checksum(int fluid, int pid, unsigned long long* checksum)
+{
+	Simulation* sim = Simulation::getCurrent();
+	const unsigned int n = sim->getFluidModel(fluid)->numActiveParticles();
+	unsigned long long cs = 0;
+	for (unsigned int i = 0; i < n; i++)
+		for (unsigned int k = 0; k < sim->numberOfNeighbors(fluid, pid, i); k++)
+			cs += (unsigned long long)(i + 1) * (sim->getNeighbor(fluid, pid, i, k) + 7u);
+	*checksum = cs;
+	return 0;
+}
+
 int ref_destroy()
 {
 	if (!Simulation::hasCurrent()) return 0;

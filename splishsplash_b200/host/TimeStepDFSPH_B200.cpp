@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <cstdlib>
 #include <stdexcept>
+#include <algorithm>
 
 using namespace SPH;
 using namespace GenParam;
@@ -37,6 +38,8 @@ struct TimeStepDFSPH_B200::Api
 	decltype(&dfsph_b200_set_params) set_params;
 	decltype(&dfsph_b200_step_host) step_host;
 	decltype(&dfsph_b200_download) download;
+	decltype(&dfsph_b200_upload) upload;
+	decltype(&dfsph_b200_neighbors) neighbors;
 };
 
 template <typename F>
@@ -66,6 +69,8 @@ void TimeStepDFSPH_B200::loadLibrary(const std::string& path)
 	resolve(m_lib, m_api->set_params, "dfsph_b200_set_params");
 	resolve(m_lib, m_api->step_host, "dfsph_b200_step_host");
 	resolve(m_lib, m_api->download, "dfsph_b200_download");
+	resolve(m_lib, m_api->upload, "dfsph_b200_upload");
+	resolve(m_lib, m_api->neighbors, "dfsph_b200_neighbors");
 	if (m_api->sizeof_real() != (int)sizeof(Real)) throw std::runtime_error("TimeStepDFSPH_B200: Real size mismatch between the reference build and " + full);
 }
 
@@ -300,6 +305,67 @@ void TimeStepDFSPH_B200::step()
 	// with the step's initial h exactly like TimeStepDFSPH::step (:248)
 	tm->setTimeStepSize(static_cast<Real>(stats.time_step_size));
 	tm->setTime(tm->getTime() + h);
+}
+
+void TimeStepDFSPH_B200::downloadNeighbors(unsigned int other, std::vector<unsigned int>& offsets, std::vector<unsigned int>& indices)
+{
+	Simulation* sim = Simulation::getCurrent();
+	FluidModel* fm = sim->getFluidModel(0);
+	const unsigned int n = fm->numActiveParticles();
+	if (!m_modelUploaded) uploadModel();
+	// host positions are authoritative: search exactly what the host sees
+	if (n > 0) check(m_api->upload(m_ctx, DFSPH_B200_FIELD_POSITION, &fm->getPosition(0)[0], n * 3 * sizeof(Real), 1), "upload position");
+	std::vector<unsigned int> counts(n), ids(n);
+	std::vector<uint64_t> off(n + 1, 0);
+	check(m_api->neighbors(m_ctx, (int)other, counts.data(), nullptr, nullptr, 0), "dfsph_b200_neighbors");
+	uint64_t total = 0;
+	for (unsigned int i = 0; i < n; i++) total += counts[i];
+	std::vector<unsigned int> idx(total ? total : 1);
+	check(m_api->neighbors(m_ctx, (int)other, counts.data(), off.data(), idx.data(), total), "dfsph_b200_neighbors");
+	if (n > 0) check(m_api->download(m_ctx, DFSPH_B200_FIELD_ID, ids.data(), n * sizeof(unsigned int), 0), "download id");
+	// device rows -> host rows (id = host index); fluid neighbour indices -> host indices
+	offsets.assign(n + 1, 0);
+	for (unsigned int r = 0; r < n; r++) offsets[ids[r] + 1] = counts[r];
+	for (unsigned int i = 0; i < n; i++) offsets[i + 1] += offsets[i];
+	indices.resize(total);
+	for (unsigned int r = 0; r < n; r++)
+	{
+		unsigned int* dst = indices.data() + offsets[ids[r]];
+		for (unsigned int k = 0; k < counts[r]; k++) dst[k] = other == 0 ? ids[idx[off[r] + k]] : idx[off[r] + k];
+		std::sort(dst, dst + counts[r]);
+	}
+}
+
+void NeighborhoodSearch_B200::find_neighbors()
+{
+	Simulation* sim = Simulation::getCurrent();
+	m_ts.downloadNeighbors(0, m_off[0], m_idx[0]);
+	m_ts.downloadNeighbors(1, m_off[1], m_idx[1]);
+	m_bodyStart.assign(1, 0u);
+	for (unsigned int b = 0; b < sim->numberOfBoundaryModels(); b++)
+		m_bodyStart.push_back(m_bodyStart.back() + static_cast<BoundaryModel_Akinci2012*>(sim->getBoundaryModel(b))->numberOfParticles());
+}
+
+std::vector<unsigned int> NeighborhoodSearch_B200::neighbor_list(unsigned int ps, unsigned int i) const
+{
+	std::vector<unsigned int> out;
+	if (ps == 0) { out.assign(m_idx[0].begin() + m_off[0][i], m_idx[0].begin() + m_off[0][i + 1]); return out; }
+	const unsigned int lo = m_bodyStart[ps - 1], hi = m_bodyStart[ps];
+	for (unsigned int k = m_off[1][i]; k < m_off[1][i + 1]; k++)
+		if (m_idx[1][k] >= lo && m_idx[1][k] < hi) out.push_back(m_idx[1][k] - lo);
+	return out;
+}
+
+unsigned int NeighborhoodSearch_B200::n_neighbors(unsigned int ps, unsigned int i) const
+{
+	if (ps == 0) return m_off[0][i + 1] - m_off[0][i];
+	return (unsigned int)neighbor_list(ps, i).size();
+}
+
+unsigned int NeighborhoodSearch_B200::neighbor(unsigned int ps, unsigned int i, unsigned int k) const
+{
+	if (ps == 0) return m_idx[0][m_off[0][i] + k];
+	return neighbor_list(ps, i)[k];
 }
 
 void Simulation_B200::useB200Solver(const std::string& libraryPath)

@@ -83,6 +83,32 @@ namespace SPH
 
 		/** also refresh the five DFSPH field mirrors after every step (default true; exporters/GUI read them) */
 		void setSyncAllFields(bool b) { m_syncAllFields = b; }
+
+		/** Neighbour lists of the fluid particles at the CURRENT host positions, in host index space (row i = host
+		 *  particle i).  other = 0: fluid neighbours (host indices); other = 1: boundary neighbours, indices into the
+		 *  concatenation of all boundary models in the order Simulation holds them.  Lists are ascending.  For tests and
+		 *  non-ported host code only -- the solver never materialises host-visible lists. */
+		void downloadNeighbors(unsigned int other, std::vector<unsigned int>& offsets, std::vector<unsigned int>& indices);
+	};
+
+	/** Facade with the PointSet accessors of CompactNSearch the reference uses (Simulation.h:456-473:
+	 *  n_neighbors / neighbor / neighbor_list), served from the device search of a TimeStepDFSPH_B200.
+	 *  Point-set numbering follows the reference: 0 = the fluid model, 1.. = the boundary models. */
+	class NeighborhoodSearch_B200
+	{
+	protected:
+		TimeStepDFSPH_B200& m_ts;
+		std::vector<unsigned int> m_off[2], m_idx[2];
+		std::vector<unsigned int> m_bodyStart;                 // first concatenated index of every boundary model
+		std::vector<std::vector<unsigned int>> m_scratch;
+	public:
+		NeighborhoodSearch_B200(TimeStepDFSPH_B200& ts) : m_ts(ts) {}
+		/** NeighborhoodSearch::find_neighbors() (Simulation.cpp:617): runs the device search on the host positions. */
+		void find_neighbors();
+		unsigned int n_neighbors(unsigned int neighborPointSet, unsigned int i) const;
+		unsigned int neighbor(unsigned int neighborPointSet, unsigned int i, unsigned int k) const;
+		/** neighbour list of fluid particle i inside point set neighborPointSet (local indices of that set) */
+		std::vector<unsigned int> neighbor_list(unsigned int neighborPointSet, unsigned int i) const;
 	};
 
 	/** Registers the method without editing Simulation.cpp: a Simulation subclass that installs TimeStepDFSPH_B200.

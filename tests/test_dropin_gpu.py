@@ -50,3 +50,38 @@ def test_reference_stack_with_b200_solver(prec):
             alpha = ref[s]["factor"].astype(np.float64) * h * h
             e = float(np.max(d[alpha > 0] / alpha[alpha > 0]))
         assert e <= tol, (s, "p / rho^2", e)
+
+
+def test_neighborhood_search_facade_matches_reference_lists():
+    """NeighborhoodSearch_B200 (CompactNSearch-style accessors served by the device search) against the reference stack's
+    own neighbour lists: counts per particle and an order-independent checksum over (i, j) pairs, fluid and boundary."""
+    import ctypes as C
+    prec = "f64"
+    if not refsim.ref_available(prec):
+        pytest.skip("oracle/_ref not present")
+    sc = scenes.dam_break("small", dtype=dtype_of(prec))
+    # reference lists (z-sort disabled so that array order = host order = particle id)
+    ref = refsim.build_ref_scene(sc, prec, kernel=4, enableZSort=0)
+    try:
+        ref.search_and_density()
+        n = ref.num_particles()
+        want = {}
+        for pid in (0, 1):
+            counts = np.empty(n, dtype=np.uint32)
+            ref.lib.ref_neighbor_counts(0, pid, counts.ctypes.data)
+            cs = C.c_ulonglong()
+            ref.lib.ref_neighbor_checksum(0, pid, C.byref(cs))
+            want[pid] = (counts, cs.value)
+    finally:
+        ref.destroy()
+    dev = refsim.build_ref_scene(sc, prec, kernel=4, b200=True, enableZSort=0)
+    try:
+        for pid in (0, 1):
+            counts = np.empty(n, dtype=np.uint32)
+            cs = C.c_ulonglong()
+            rc = dev.lib.ref_b200_neighbor_counts(pid, counts.ctypes.data, C.byref(cs))
+            assert rc == 0, dev.lib.ref_last_error()
+            assert np.array_equal(counts, want[pid][0])
+            assert cs.value == want[pid][1]
+    finally:
+        dev.destroy()
