@@ -71,6 +71,10 @@ PROF_CLASSES = ["sort", "build_neighbors", "init_sweep", "accel", "jacobi_div", 
 
 
 def lib_path(precision: str) -> str:
+    # DFSPH_B200_LIB_<PRECISION> overrides the in-tree library (tuning experiments with alternative builds)
+    override = os.environ.get(f"DFSPH_B200_LIB_{precision.upper()}")
+    if override:
+        return override
     return os.path.join(_PKG, f"libdfsph_b200_{precision}.so")
 
 

@@ -160,6 +160,8 @@ struct SolverParams {
     Real viscosity, viscosity_boundary;
 };
 
+#ifndef DFSPH_BLOCK
 #define DFSPH_BLOCK 256
+#endif
 #define DFSPH_TILE 32
 #define DFSPH_PAD 4u     /* neighbour lists are padded to multiples of this (>= the sweep unroll factors) */

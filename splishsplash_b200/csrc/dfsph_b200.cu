@@ -1060,13 +1060,13 @@ static int run_solver(dfsph_b200_ctx* c)
     auto launch_jacobi = [&](int solve, const unsigned* list, unsigned list_n, const unsigned char* skip, unsigned base, int finalize, int seq,
                              GhostWait gw = GhostWait{nullptr, nullptr, 0u}, const PeerReduce* prp = nullptr) {
         const PeerReduce& pr = prp ? *prp : no_red;
-        const unsigned g = list ? std::max(div_up(list_n, DFSPH_BLOCK), 1u) : grid;
+        const unsigned g = std::max(div_up(list ? list_n : n, DFSPH_JACOBI_BLOCK), 1u);
         const bool keep = c->profiling;
         if (list) c->profiling = false;
         ProfScope ps(c, solve == SOLVE_DIV ? DFSPH_B200_PROF_JACOBI_DIV : DFSPH_B200_PROF_JACOBI_PRESS, seq);
         c->profiling = keep;
-        if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize, gw, pr);
-        else k_jacobi<MODE, SOLVE_PRESS><<<g, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize, gw, pr);
+        if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<g, DFSPH_JACOBI_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize, gw, pr);
+        else k_jacobi<MODE, SOLVE_PRESS><<<g, DFSPH_JACOBI_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl, c->partial, list, list_n, skip, base, finalize, gw, pr);
         c->launches++;
     };
     // multi-GPU: ghost kappa that arrived on the communication stream is moved into pos[n ..] on the main stream
@@ -1114,7 +1114,7 @@ static int run_solver(dfsph_b200_ctx* c)
                 } else {
                     // boundary-first: the export particles' results travel while the interior is being computed
                     if (kappa_in_flight) { int rl = land_ghost_kappa(); if (rl) return rl; }
-                    const unsigned nbB = std::max(div_up(c->n_exp_all, DFSPH_BLOCK), 1u);
+                    const unsigned nbB = std::max(div_up(c->n_exp_all, DFSPH_JACOBI_BLOCK), 1u);
                     if (c->n_exp_all) launch_accel(c->exp_all, c->n_exp_all, nullptr, -1);
                     CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
                     { int rg = exchange_ghosts_async(c, c->acc, c->acc + c->n, c->ev_a, c->ev_a2); if (rg) return rg; }
