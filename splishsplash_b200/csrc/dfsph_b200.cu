@@ -47,6 +47,7 @@ struct dfsph_b200_ctx {
     unsigned *cell_count = nullptr, *cell_start = nullptr, *scan_partial = nullptr;
     unsigned keys_cap = 0, scratch_cap = 0;
     bool tables_valid = false;   // neighbour table matches pos[cur_pos]
+    cudaTextureObject_t acc_tex = 0;
 
     // boundary (static Akinci2012 particles, all bodies concatenated)
     std::vector<Real4> h_bpos;
@@ -356,6 +357,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     for (int k = 0; k < 2; ++k) {
         cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->kappa[k]); cudaFree(c->kappa_v[k]); cudaFree(c->id[k]); cudaFree(c->state[k]);
     }
+    if (c->acc_tex) cudaDestroyTextureObject(c->acc_tex);
     cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
     cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b); cudaFree(c->tcnt_f); cudaFree(c->tcnt_b);
     cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
@@ -590,6 +592,19 @@ static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
         if (dev_alloc(c, &c->state[k], cap)) return DFSPH_B200_ERR_CUDA;
     }
     if (dev_alloc(c, &c->acc, cap + c->ghost_cap + 1)) return DFSPH_B200_ERR_CUDA;
+#if !DFSPH_REAL_IS_DOUBLE
+    {
+        if (c->acc_tex) { cudaDestroyTextureObject(c->acc_tex); c->acc_tex = 0; }
+        const size_t elems = (size_t)cap + c->ghost_cap + 1;
+        if (elems < (1ull << 27) && !getenv("DFSPH_B200_NO_TEX")) {   // linear textures address at most 2^27 texels
+            cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = c->acc;
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = elems * sizeof(float4);
+            cudaTextureDesc td; memset(&td, 0, sizeof(td)); td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&c->acc_tex, &rd, &td, nullptr) != cudaSuccess) { c->acc_tex = 0; cudaGetLastError(); }
+        }
+    }
+#endif
     if (dev_alloc(c, &c->bgrad, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->density, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->factor, cap)) return DFSPH_B200_ERR_CUDA;
@@ -807,6 +822,7 @@ static FluidArrays fluid_arrays(dfsph_b200_ctx* c)
     f.state = c->state[c->cur]; f.nnbr = c->nnbr;
     f.tab_f = c->tab_f; f.cnt_f = c->cnt_f; f.tab_b = c->tab_b; f.cnt_b = c->cnt_b; f.tcnt_f = c->tcnt_f; f.tcnt_b = c->tcnt_b;
     f.Kf = c->Kf; f.Kb = c->Kb; f.n = c->n;
+    f.acc_tex = c->acc_tex;
     return f;
 }
 

@@ -60,6 +60,7 @@ struct FluidArrays {
     const unsigned* tcnt_b;
     unsigned Kf, Kb;
     unsigned n;
+    cudaTextureObject_t acc_tex;   // float build: pass B fetches a_j through the texture path (0 = plain loads)
 };
 
 __device__ __forceinline__ const unsigned* tab_ptr(const unsigned* tab, unsigned K, unsigned i)
@@ -321,10 +322,25 @@ template <int MODE>
 struct JacobiF {
     struct Data { Real4 x, a; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* acc; const SphConst& c;
+    cudaTextureObject_t acc_tex;
     Real4 xi, ai;
     Real sum;
-    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), xi(xi_), ai(ai_), sum(0) {}
-    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.a = ld_gather(acc + j); return d; }
+    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), acc_tex(f.acc_tex), xi(xi_), ai(ai_), sum(0) {}
+    __device__ __forceinline__ Data load(unsigned j) const
+    {
+        Data d;
+        d.x = ld_plain(pos + j);
+#if DFSPH_REAL_IS_DOUBLE
+        d.a = ld_gather(acc + j);
+#else
+        // The two scattered gathers of pass B go through different L1 front ends (LSU for x_j, TEX for a_j): the LSU data
+        // pipe is the limiter of this kernel (ncu: 89-92 %), and the microbenchmark (tools/micro/tex_bench.cu) shows the
+        // mixed form is ~11 % cheaper than two LSU gathers.
+        if (acc_tex) { const float4 t = tex1Dfetch<float4>(acc_tex, (int)j); d.a = make_real4(t.x, t.y, t.z, t.w); }
+        else d.a = ld_gather(acc + j);
+#endif
+        return d;
+    }
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
