@@ -592,19 +592,23 @@ static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
         if (dev_alloc(c, &c->state[k], cap)) return DFSPH_B200_ERR_CUDA;
     }
     if (dev_alloc(c, &c->acc, cap + c->ghost_cap + 1)) return DFSPH_B200_ERR_CUDA;
-#if !DFSPH_REAL_IS_DOUBLE
     {
+        // pass B reads a_j through the texture path (16 B texels: one per particle in the float build, two in the double build)
         if (c->acc_tex) { cudaDestroyTextureObject(c->acc_tex); c->acc_tex = 0; }
-        const size_t elems = (size_t)cap + c->ghost_cap + 1;
-        if (elems < (1ull << 27) && !getenv("DFSPH_B200_NO_TEX")) {   // linear textures address at most 2^27 texels
+        const size_t texels = ((size_t)cap + c->ghost_cap + 1) * (sizeof(Real4) / 16);
+        if (texels < (1ull << 27) && !getenv("DFSPH_B200_NO_TEX")) {   // linear textures address at most 2^27 texels
             cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
             rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = c->acc;
-            rd.res.linear.desc = cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = elems * sizeof(float4);
+#if DFSPH_REAL_IS_DOUBLE
+            rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+#else
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+#endif
+            rd.res.linear.sizeInBytes = texels * 16;
             cudaTextureDesc td; memset(&td, 0, sizeof(td)); td.readMode = cudaReadModeElementType;
             if (cudaCreateTextureObject(&c->acc_tex, &rd, &td, nullptr) != cudaSuccess) { c->acc_tex = 0; cudaGetLastError(); }
         }
     }
-#endif
     if (dev_alloc(c, &c->bgrad, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->density, cap)) return DFSPH_B200_ERR_CUDA;
     if (dev_alloc(c, &c->factor, cap)) return DFSPH_B200_ERR_CUDA;

@@ -331,7 +331,10 @@ struct JacobiF {
         Data d;
         d.x = ld_plain(pos + j);
 #if DFSPH_REAL_IS_DOUBLE
-        d.a = ld_gather(acc + j);
+        if (acc_tex) {   // 32 B record = two 16 B texels
+            const int4 t0 = tex1Dfetch<int4>(acc_tex, (int)(2u * j)), t1 = tex1Dfetch<int4>(acc_tex, (int)(2u * j + 1u));
+            d.a = make_real4(__hiloint2double(t0.y, t0.x), __hiloint2double(t0.w, t0.z), __hiloint2double(t1.y, t1.x), __hiloint2double(t1.w, t1.z));
+        } else d.a = ld_gather(acc + j);
 #else
         // The two scattered gathers of pass B go through different L1 front ends (LSU for x_j, TEX for a_j): the LSU data
         // pipe is the limiter of this kernel (ncu: 89-92 %), and the microbenchmark (tools/micro/tex_bench.cu) shows the
