@@ -45,7 +45,14 @@ ALGO_BYTES = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
 # keyed by (kernel class, precision, particles); None when no capture exists for that configuration
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # profiles/r1_ncu_10M_f32_v2_summary.csv (ncu --set full, tools/prof_run.py f32 10M 2)
+    ("jacobi_press", "f32", "10M"): 2.0707e9,
+    ("jacobi_div", "f32", "10M"): 2.0707e9,
+    ("accel", "f32", "10M"): 1.6501e9,
+    ("build_neighbors", "f32", "10M"): 1.9677e9,
+    ("init_sweep", "f32", "10M"): 2.3788e9,
+}
 
 
 def load_peaks():

@@ -298,8 +298,15 @@ __device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphCo
 // Multi-GPU overlap: the particles a neighbour rank needs (export list) are processed first by a launch over `list`,
 // their values travel on the communication stream while a second launch over all particles skips them (`skip`).
 // Single GPU: list == nullptr, skip == nullptr.
+#ifndef DFSPH_ACCEL_MIN_BLOCKS
+#if DFSPH_REAL_IS_DOUBLE
+#define DFSPH_ACCEL_MIN_BLOCKS 1
+#else
+#define DFSPH_ACCEL_MIN_BLOCKS 8    /* 32 registers, full occupancy: -3 % */
+#endif
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_accel(FluidArrays f, SphConst c, const Ctrl* __restrict__ ctrl,
+__global__ void __launch_bounds__(DFSPH_BLOCK, DFSPH_ACCEL_MIN_BLOCKS) k_accel(FluidArrays f, SphConst c, const Ctrl* __restrict__ ctrl,
                                                          const unsigned* __restrict__ list, unsigned list_n, const unsigned char* __restrict__ skip,
                                                          GhostWait gw)
 {
@@ -382,8 +389,15 @@ __device__ __forceinline__ void solve_control(Ctrl* ctrl, const SolverParams& sp
 
 // list / skip: see k_accel.  partial_base: first slot of this launch in `partial`; finalize: this launch elects the last
 // block, which sums partial[0 .. partial_base + gridDim.x) (the export-list launch runs first with finalize = 0).
+#ifndef DFSPH_JACOBI_MIN_BLOCKS
+#if DFSPH_REAL_IS_DOUBLE
+#define DFSPH_JACOBI_MIN_BLOCKS 1   /* the double build needs ~64 registers; forcing more blocks spills */
+#else
+#define DFSPH_JACOBI_MIN_BLOCKS 3   /* 40 registers, 75 % occupancy: 0.97 -> 0.89 ms at 10 M (4 blocks spill: 1.27 ms) */
+#endif
+#endif
 template <int MODE, int SOLVE>
-__global__ void __launch_bounds__(DFSPH_JACOBI_BLOCK) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial,
+__global__ void __launch_bounds__(DFSPH_JACOBI_BLOCK, DFSPH_JACOBI_MIN_BLOCKS) k_jacobi(FluidArrays f, SphConst c, SolverParams sp, Ctrl* ctrl, double* __restrict__ partial,
                                                           const unsigned* __restrict__ list, unsigned list_n, const unsigned char* __restrict__ skip,
                                                           unsigned partial_base, int finalize, GhostWait gw, PeerReduce pr)
 {
