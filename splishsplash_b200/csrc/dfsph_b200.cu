@@ -432,7 +432,16 @@ static int setup_grid(dfsph_b200_ctx* c)
     bool given = false;
     for (int k = 0; k < 3; ++k) if (c->cfg.domain_max[k] > c->cfg.domain_min[k]) given = true;
     const double S = (double)c->sph.R * (1.0 + 1.0e-5);
-    if (given) { for (int k = 0; k < 3; ++k) { lo[k] = c->cfg.domain_min[k]; hi[k] = c->cfg.domain_max[k]; } }
+    if (given) {
+        for (int k = 0; k < 3; ++k) { lo[k] = c->cfg.domain_min[k]; hi[k] = c->cfg.domain_max[k]; }
+        if (c->multi) {
+            // every rank only needs cells for its own slab plus the ghost / boundary halo (2 cells): the cell tables stay
+            // proportional to the slab instead of the global domain (cell keys are rank-local)
+            const int a = c->slab_axis;
+            lo[a] = std::max(lo[a], c->slab_lo - 2.0 * S);
+            hi[a] = std::min(hi[a], c->slab_hi + 2.0 * S);
+        }
+    }
     else {
         if (!c->bb_valid) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "no particles: cannot derive the cell grid");
         for (int k = 0; k < 3; ++k) { lo[k] = c->bb_min[k] - S; hi[k] = c->bb_max[k] + S; }
