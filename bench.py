@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--cpu-sample", default="1M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = one block of --particles per GPU (default); strong = one block of --particles cut into N slabs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -203,7 +205,10 @@ def main():
         # weak scaling: `world` blocks of the named size side by side in one tank, one x-slab per GPU, ghost exchange and
         # migration over NCCL inside the library (splishsplash_b200/csrc/multi_gpu.cuh)
         from splishsplash_b200 import parallel
-        sc = scenes.dam_break_weak(rank, world, args.particles, dtype=dt)
+        if args.scaling == "weak":
+            sc = scenes.dam_break_weak(rank, world, args.particles, dtype=dt)
+        else:
+            sc = scenes.dam_break_slab(rank, world, args.particles, dtype=dt)
         ts = parallel.build_b200_slab(sc, args.precision, rank, world, device=local_rank, **solver_params())
     n = ts.num_particles
     n_global = n if world == 1 else sc["global_particles"]
@@ -293,7 +298,7 @@ def main():
         line = {
             "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": dict(cfg, parallelism=("single GPU" if world == 1 else
                                              f"{world} x-slabs, one per GPU, NCCL ghost exchange (x,v per step; kappa, a per iteration) + migration")),
             "e2e": {"value": n_global * args.e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -160,11 +160,49 @@ def dam_break(counts="tiny", radius=0.025, dtype=np.float32, tank_x_factor=3.0, 
             "tank_min": tmin, "tank_max": tmax}
 
 
-def dam_break_weak(rank, world, counts="10M", radius=0.025, dtype=np.float32, tank_x_factor=3.0, tank_y_factor=1.5,
+def dam_break_slab(rank, world, global_counts, radius=0.025, dtype=np.float32, tank_x_factor=3.0, tank_y_factor=1.5,
                    spacing_factor=1.5, halo_cells=2.0, axis=2):
-    """Weak-scaling scene: `world` blocks of the named size side by side along `axis` in one tank; rank
-    r generates ONLY its own block (global particle ids), its slab [lo, hi) along `axis` and the boundary particles
-    within `halo_cells` cells of the slab.  The global scene is never materialised.
+    """Per-rank portion of ONE dam-break block of `global_counts` lattice particles cut into `world` slabs along `axis`
+    (strong scaling, BASELINE config 4; also the building block of the weak-scaling scene).  Rank r generates ONLY its own
+    lattice planes (global particle ids), its slab [lo, hi) and the boundary particles within `halo_cells` cells of the
+    slab; the global scene is never materialised."""
+    if isinstance(global_counts, str):
+        global_counts = NAMED_BLOCKS[global_counts]
+    if axis not in (0, 2):
+        raise ValueError("axis 0 (x) or 2 (z)")
+    g = [int(c) for c in global_counts]
+    dt = np.dtype(dtype).type
+    d = 2.0 * radius
+    block = np.array([(g[0] + 1) * d, (g[1] + 1) * d, (g[2] + 1) * d])
+    tmin = np.zeros(3)
+    tmax = np.array([tank_x_factor * block[0], tank_y_factor * block[1], block[2]])
+    # lattice planes of this rank along the slab axis (as even as possible)
+    cuts = [(g[axis] * r) // world for r in range(world + 1)]
+    idx = [np.arange(g[0]), np.arange(g[1]), np.arange(g[2])]
+    idx[axis] = np.arange(cuts[rank], cuts[rank + 1])
+    # the same position arithmetic as fluid_lattice for the global lattice (index * diam + start, in Real)
+    diam = dt(2.0) * dt(radius)
+    ax = [(i.astype(dtype) * diam + dt(d)).astype(dtype) for i in idx]
+    x = np.empty((len(idx[0]), len(idx[1]), len(idx[2]), 3), dtype=dtype)
+    x[..., 0] = ax[0][:, None, None]
+    x[..., 1] = ax[1][None, :, None]
+    x[..., 2] = ax[2][None, None, :]
+    ids = ((idx[0][:, None, None].astype(np.int64) * g[1] + idx[1][None, :, None]) * g[2] + idx[2][None, None, :])
+    # slab faces half-way between lattice planes
+    face = lambda plane: d + (plane - 0.5) * d
+    lo = -1.0e300 if rank == 0 else face(cuts[rank])
+    hi = 1.0e300 if rank == world - 1 else face(cuts[rank + 1])
+    cell = 4.0 * radius * (1.0 + 1.0e-5)
+    bnd = box_boundary(tmin, tmax, radius, dtype, spacing_factor, axis_range=(axis, lo - halo_cells * cell, hi + halo_cells * cell))
+    return {"fluid_x": x.reshape(-1, 3), "fluid_ids": ids.reshape(-1).astype(np.uint32), "boundary_x": bnd,
+            "radius": float(radius), "counts": tuple(len(i) for i in idx), "slab": (lo, hi), "slab_axis": axis,
+            "domain": (tmin - cell, tmax + cell), "tank_min": tmin, "tank_max": tmax,
+            "global_particles": int(g[0]) * g[1] * g[2], "global_counts": tuple(g)}
+
+
+def dam_break_weak(rank, world, counts="10M", radius=0.025, dtype=np.float32, axis=2, **kw):
+    """Weak-scaling scene: `world` blocks of the named size side by side along `axis` in one tank, one
+    slab per rank (see dam_break_slab).
 
     axis = 2 (default): the dam is replicated across the tank (z), slabs are perpendicular to the flow, so every GPU
     sees the same dam-break physics for the whole run (same iteration counts as the single-GPU block, no load drift).
@@ -172,36 +210,9 @@ def dam_break_weak(rank, world, counts="10M", radius=0.025, dtype=np.float32, ta
     system needs more Jacobi iterations and the fluid drifts towards the last ranks as the dam collapses."""
     if isinstance(counts, str):
         counts = NAMED_BLOCKS[counts]
-    if axis not in (0, 2):
-        raise ValueError("axis 0 (x) or 2 (z)")
-    nx, ny, nz = counts
-    dt = np.dtype(dtype).type
-    d = 2.0 * radius
-    g = [nx, ny, nz]
+    g = list(counts)
     g[axis] *= world
-    block = np.array([(g[0] + 1) * d, (g[1] + 1) * d, (g[2] + 1) * d])
-    tmin = np.zeros(3)
-    tmax = np.array([tank_x_factor * block[0], tank_y_factor * block[1], block[2]])
-    # the same position arithmetic as fluid_lattice for the global lattice (index * diam + start, in Real)
-    diam = dt(2.0) * dt(radius)
-    idx = [np.arange(nx), np.arange(ny), np.arange(nz)]
-    idx[axis] = np.arange(rank * counts[axis], (rank + 1) * counts[axis])
-    ax = [(i.astype(dtype) * diam + dt(d)).astype(dtype) for i in idx]
-    x = np.empty((nx, ny, nz, 3), dtype=dtype)
-    x[..., 0] = ax[0][:, None, None]
-    x[..., 1] = ax[1][None, :, None]
-    x[..., 2] = ax[2][None, None, :]
-    ids = ((idx[0][:, None, None].astype(np.int64) * g[1] + idx[1][None, :, None]) * g[2] + idx[2][None, None, :])
-    # slab faces half-way between lattice planes
-    face = lambda k: d + (k * counts[axis] - 0.5) * d
-    lo = -1.0e300 if rank == 0 else face(rank)
-    hi = 1.0e300 if rank == world - 1 else face(rank + 1)
-    cell = 4.0 * radius * (1.0 + 1.0e-5)
-    bnd = box_boundary(tmin, tmax, radius, dtype, spacing_factor, axis_range=(axis, lo - halo_cells * cell, hi + halo_cells * cell))
-    return {"fluid_x": x.reshape(-1, 3), "fluid_ids": ids.reshape(-1).astype(np.uint32), "boundary_x": bnd,
-            "radius": float(radius), "counts": tuple(counts), "slab": (lo, hi), "slab_axis": axis,
-            "domain": (tmin - cell, tmax + cell), "tank_min": tmin, "tank_max": tmax,
-            "global_particles": int(g[0]) * g[1] * g[2], "global_counts": tuple(g)}
+    return dam_break_slab(rank, world, g, radius, dtype, axis=axis, **kw)
 
 
 def rw_state_scene(dtype=np.float32):

@@ -116,3 +116,16 @@ def test_weak_scaling_scene_tiles_the_global_block(axis):
     full = scenes.box_boundary(parts[0]["tank_min"], parts[0]["tank_max"], 0.025, np.float32)
     got = np.unique(np.concatenate([p["boundary_x"] for p in parts]), axis=0)
     assert np.array_equal(got, np.unique(full, axis=0))
+
+
+def test_strong_scaling_slabs_tile_one_block():
+    world = 3
+    parts = [scenes.dam_break_slab(r, world, (10, 12, 10), dtype=np.float64, axis=2) for r in range(world)]
+    ids = np.concatenate([p["fluid_ids"] for p in parts])
+    assert len(np.unique(ids)) == len(ids) == 1200 == parts[0]["global_particles"]
+    g = scenes.fluid_lattice((10, 12, 10), 0.025, (0.05, 0.05, 0.05), np.float64)
+    x = np.empty_like(g)
+    for p in parts:
+        x[p["fluid_ids"]] = p["fluid_x"]
+    assert np.array_equal(x, g)
+    assert [p["counts"][2] for p in parts] == [3, 3, 4]
