@@ -1564,6 +1564,9 @@ int dfsph_b200_comm_init(dfsph_b200_ctx* c, const void* id128 /* the 256 bytes o
     if (!given) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "multi-GPU runs need an explicit cell-grid domain (config.domain_min/max) shared by all ranks");
     if (!(slab_hi > slab_lo)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "empty slab");
     if (axis < 0 || axis > 2) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "slab axis must be 0, 1 or 2");
+    // ghosts only ever come from the two adjacent ranks: an interior slab must be at least one cell (support radius) wide
+    if (slab_lo > -1e299 && slab_hi < 1e299 && (slab_hi - slab_lo) < 4.0 * c->cfg.particle_radius * (1.0 + 1.0e-5))
+        CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "slab [%g, %g) is narrower than one support radius", slab_lo, slab_hi);
     c->slab_axis = axis;
     if (world == 1) return DFSPH_B200_OK;
     std::string err;
