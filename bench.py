@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", default="1M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps on one GPU (same window as the device-resident run), 10 on N>1")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = one block of --particles per GPU (default); strong = one block of --particles cut into N slabs")
     args = ap.parse_args()
@@ -245,34 +245,51 @@ def main():
         ms = float(t.item())
 
     # ---- end-to-end through host buffers (pinned): H2D of x, v and D2H of x, v, density inside the timed region
-    n = ts.num_particles          # (migration may have changed the local count)
-    x = ts.pinned((n, 3))
-    v = ts.pinned((n, 3))
-    rho = ts.pinned((n,))
+    e2e_iters = []
     if world == 1:
-        x[:] = ts.field("position")
-        v[:] = ts.field("velocity")
-        e2e_step = lambda: ts.step_host(x, v, rho)
+        # same workload, same window: a fresh context replays warm-up + timed steps, every step through step_host
+        ts.close()
+        ts = build_b200_scene(sc, args.precision, device=local_rank, **solver_params())
+        n = ts.num_particles
+        x = ts.pinned((n, 3))
+        v = ts.pinned((n, 3))
+        rho = ts.pinned((n,))
+        x[:] = sc["fluid_x"]
+        v[:] = sc["fluid_v"] if sc.get("fluid_v") is not None else 0
+        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else args.steps
+        e2e_warm = args.warmup
+
+        def e2e_step():
+            st = ts.step_host(x, v, rho)
+            e2e_iters.append((st.iterations_v, st.iterations))
     else:
         # multi-GPU: the host buffers are in device order (ids are global); upload, step, download
+        n = ts.num_particles          # (migration may have changed the local count)
+        x = ts.pinned((n, 3))
+        v = ts.pinned((n, 3))
+        rho = ts.pinned((n,))
         x[:] = ts.field("position", by_id=False)
         v[:] = ts.field("velocity", by_id=False)
+        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else 10
+        e2e_warm = 2
 
         def e2e_step():
             m = ts.num_particles
             ts.set_field("position", x[:m], by_id=False)
             ts.set_field("velocity", v[:m], by_id=False)
-            ts.step(1)
+            st = ts.step(1)
+            e2e_iters.append((st.iterations_v, st.iterations))
             m2 = min(ts.num_particles, n)
             x[:m2] = ts.field("position", by_id=False)[:m2]
             v[:m2] = ts.field("velocity", by_id=False)[:m2]
             rho[:m2] = ts.field("density", by_id=False)[:m2]
-    for _ in range(2):
+    for _ in range(e2e_warm):
         e2e_step()
     barrier()
+    del e2e_iters[:]
     t0 = time.perf_counter()
     ts.timer_start()
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         e2e_step()
     ms_e2e = ts.timer_stop()
     wall_e2e = (time.perf_counter() - t0) * 1000.0
@@ -301,8 +318,10 @@ def main():
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": dict(cfg, parallelism=("single GPU" if world == 1 else
                                              f"{world} x-slabs, one per GPU, NCCL ghost exchange (x,v per step; kappa, a per iteration) + migration")),
-            "e2e": {"value": n_global * args.e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+            "e2e": {"value": n_global * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "warmup": e2e_warm, "ms_per_step": ms_e2e / e2e_steps,
+                    "mean_iterations": {"divergence": float(np.mean([i[0] for i in e2e_iters])),
+                                        "pressure": float(np.mean([i[1] for i in e2e_iters]))}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -74,6 +74,12 @@ struct dfsph_b200_ctx {
     unsigned pred_iter = 2, pred_iter_v = 1;
     unsigned launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // step_host overlap: v arrives on copy_stream while the search runs; density leaves as soon as the init sweep wrote it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy_in = nullptr, ev_density = nullptr;
+    const Real* late_vel_stage = nullptr;     // staged host velocities (id order), landed after the reorder
+    Real* early_density_stage = nullptr;      // device staging + host destination of the early density download
+    void* early_density_host = nullptr;
     void* stage = nullptr;       // device staging for AoS transfers
     size_t stage_bytes = 0;
 
@@ -374,6 +380,9 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     cudaFree(c->xcnt); cudaFree(c->exp_all); cudaFree(c->is_export); cudaFree(c->ghost_stage);
     if (c->comm2 && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm2);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_copy_in) cudaEventDestroy(c->ev_copy_in);
+    if (c->ev_density) cudaEventDestroy(c->ev_density);
     if (c->ev_a) { cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_a2); cudaEventDestroy(c->ev_k); cudaEventDestroy(c->ev_k2); }
     if (c->h_xcnt) cudaFreeHost(c->h_xcnt);
     if (c->comm && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm);
@@ -1075,6 +1084,14 @@ static int run_solver(dfsph_b200_ctx* c)
     if (div) k_init_sweep<MODE, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl);
     else k_init_sweep<MODE, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->bpos, c->ctrl); }
     c->launches++;
+    if (c->early_density_host && n > 0) {   // step_host: the density of this step is final here; send it home behind the solver
+        CUDA_TRY(c, cudaEventRecord(c->ev_density, st));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_density, 0));
+        k_pack1<Real><<<div_up(n, 256), 256, 0, c->copy_stream>>>(c->density, c->early_density_stage, n, c->id[c->cur]);
+        CUDA_TRY(c, cudaMemcpyAsync(c->early_density_host, c->early_density_stage, (size_t)n * sizeof(Real), cudaMemcpyDeviceToHost, c->copy_stream));
+        c->launches++;
+        c->early_density_host = nullptr;
+    }
 
     PeerReduce no_red; memset(&no_red, 0, sizeof(no_red));
     auto launch_accel = [&](const unsigned* list, unsigned list_n, const unsigned char* skip, int seq, GhostWait gw = GhostWait{nullptr, nullptr, 0u}) {
@@ -1238,6 +1255,12 @@ static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
     k_step_begin<<<1, 1, 0, st>>>(c->ctrl);
     c->launches++;
     if (!c->tables_valid) { rc = run_search(c); if (rc) return rc; }
+    if (c->late_vel_stage) {   // step_host: the velocity upload overlapped the search; scatter it into the sorted order now
+        CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_copy_in, 0));
+        k_unpack3<<<std::max(div_up(c->n, 256), 1u), 256, 0, st>>>(c->late_vel_stage, c->vel[c->cur], c->n, c->id[c->cur], 0);
+        c->launches++;
+        c->late_vel_stage = nullptr;
+    }
     CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
 #if DFSPH_REAL_IS_DOUBLE
     if (c->solver_mode == KM_CUBIC) rc = run_solver<KM_CUBIC>(c);
@@ -1385,29 +1408,39 @@ int dfsph_b200_step_host(dfsph_b200_ctx* c, void* x_inout, void* v_inout, void* 
     const size_t b3 = (size_t)n * 3 * sizeof(Real);
     { int rc = ensure_stage(c, 2 * b3 + (size_t)n * sizeof(Real)); if (rc) return rc; }
     cudaStream_t st = c->stream;
+    if (!c->copy_stream) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copy_in, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_density, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = c->copy_stream;
     Real* sx = (Real*)c->stage;
     Real* sv = sx + (size_t)n * 3;
     Real* sd = sv + (size_t)n * 3;
     const unsigned g = std::max(div_up(n, 256), 1u);
     if (n > 0) {
+        // x first (the search needs it); v follows on the copy stream and is scattered after the reorder (do_step)
         CUDA_TRY(c, cudaMemcpyAsync(sx, x_inout, b3, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(c, cudaMemcpyAsync(sv, v_inout, b3, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaEventRecord(c->ev_copy_in, st));
         k_unpack3<<<g, 256, 0, st>>>(sx, c->pos[c->cur_pos], n, c->id[c->cur], 0);
-        k_unpack3<<<g, 256, 0, st>>>(sv, c->vel[c->cur], n, c->id[c->cur], 0);
+        c->tables_valid = false;
+        CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_copy_in, 0));   // keep the two uploads back to back on the H2D engine
+        CUDA_TRY(c, cudaMemcpyAsync(sv, v_inout, b3, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(c, cudaEventRecord(c->ev_copy_in, cs));
+        c->late_vel_stage = sv;
+        if (density_out) { c->early_density_stage = sd; c->early_density_host = density_out; }
     }
     int rc = do_step(c, stats);
-    if (rc) return rc;
+    c->late_vel_stage = nullptr; c->early_density_host = nullptr;
+    if (rc) { cudaStreamSynchronize(cs); return rc; }
     if (n > 0) {
         k_pack3<<<g, 256, 0, st>>>(c->pos[c->cur_pos], sx, n, c->id[c->cur]);
-        k_pack3<<<g, 256, 0, st>>>(c->vel[c->cur], sv, n, c->id[c->cur]);
         CUDA_TRY(c, cudaMemcpyAsync(x_inout, sx, b3, cudaMemcpyDeviceToHost, st));
+        k_pack3<<<g, 256, 0, st>>>(c->vel[c->cur], sv, n, c->id[c->cur]);
         CUDA_TRY(c, cudaMemcpyAsync(v_inout, sv, b3, cudaMemcpyDeviceToHost, st));
-        if (density_out) {
-            k_pack1<Real><<<g, 256, 0, st>>>(c->density, sd, n, c->id[c->cur]);
-            CUDA_TRY(c, cudaMemcpyAsync(density_out, sd, (size_t)n * sizeof(Real), cudaMemcpyDeviceToHost, st));
-        }
-        if (stats) stats->gpu_launches += density_out ? 5 : 4;
+        if (stats) stats->gpu_launches += 3;   // x unpack + two packs (the late v unpack and the density pack are counted in do_step)
     }
+    CUDA_TRY(c, cudaStreamSynchronize(cs));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     return DFSPH_B200_OK;
 }
