@@ -37,7 +37,9 @@ typedef enum {
 } dfsph_b200_status;
 
 /* Kernel ids use the reference's enum values (SPlisHSPlasH/Simulation.cpp:215-253). */
-enum { DFSPH_B200_KERNEL_CUBIC = 0, DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC = 4 };
+/* Simulation "kernel" / "gradKernel" ids of the 3-D build (Simulation.cpp:221-228, 241-248) */
+enum { DFSPH_B200_KERNEL_CUBIC = 0, DFSPH_B200_KERNEL_WENDLAND_QUINTIC_C2 = 1, DFSPH_B200_KERNEL_POLY6 = 2,
+       DFSPH_B200_KERNEL_SPIKY = 3, DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC = 4 };
 
 /* Particle fields, named after the reference's FieldDescription names
  * (SPlisHSPlasH/FluidModel.cpp:60-66, SPlisHSPlasH/DFSPH/TimeStepDFSPH.cpp:49-53). */
@@ -58,8 +60,10 @@ typedef enum {
 
 typedef struct {
     int32_t device;                 /* CUDA device ordinal */
-    int32_t kernel;                 /* Simulation "kernel"/"gradKernel": 0 cubic, 4 precomputed cubic (DFSPH default,
-                                       Simulation.cpp:579-582).  Honoured by the f64 library everywhere; the f32 library
+    int32_t kernel;                 /* Simulation "kernel": 0 cubic, 1 Wendland quintic C2, 2 Poly6, 3 Spiky, 4 precomputed
+                                       cubic (DFSPH default, Simulation.cpp:579-582; setKernel :338-393).  Honoured by
+                                       the f64 library everywhere (the pairs 0/0 and 4/4 have dedicated kernels, every
+                                       other kernel/grad_kernel pair runs a run-time switched variant); the f32 library
                                        mirrors the AVX build: solver sums always use the analytic cubic kernel
                                        (TimeStep.cpp:80, TimeStepDFSPH.cpp:789) and `kernel` only selects the kernel of
                                        the boundary-volume initialisation (BoundaryModel_Akinci2012.cpp:61-72). */
@@ -71,6 +75,8 @@ typedef struct {
     double domain_max[3];           /*   the first step (particles that leave it are clamped to the edge cells) */
     int32_t rank;                   /* multi-GPU slab decomposition along x: this context's slab (0 for single GPU) */
     int32_t world_size;             /* number of slabs (1 for single GPU) */
+    int32_t grad_kernel;            /* Simulation "gradKernel" (setGradKernel, Simulation.cpp:306-336), same ids;
+                                       -1 (dfsph_b200_default_config) = same as `kernel` */
 } dfsph_b200_config;
 
 /* TimeStepDFSPH / Simulation / TimeManager parameters, same names and defaults as the reference

@@ -45,7 +45,7 @@ struct Sim {
     Real gravity[3] = { 0, static_cast<Real>(-9.81), 0 };
     int cflMethod = 1;
     Real cflFactor = 0.5f, cflMin = static_cast<Real>(0.0001), cflMax = static_cast<Real>(0.005);
-    int kernel = 4;
+    int kernel = 4, gradKernel = 4;   // Simulation "kernel" / "gradKernel" (Simulation.cpp:306-393)
     // TimeStepDFSPH parameters (TimeStepDFSPH.cpp:28-41)
     unsigned minIter = 2, maxIter = 100, maxIterV = 100;
     Real maxError = static_cast<Real>(0.01), maxErrorV = static_cast<Real>(0.1);
@@ -55,7 +55,8 @@ struct Sim {
     std::vector<V3> acc;           // non-pressure accelerations (FluidModel::m_a)
     unsigned iterations = 0, iterationsV = 0;
     // kernel constants
-    Real k = 0, l = 0, W_zero = 0, invR = 0, invR2 = 0, lutInvStep = 0;
+    Real k = 0, l = 0, W_zero = 0, simW_zero = 0, invR = 0, invR2 = 0, lutInvStep = 0;
+    Real wend_k = 0, wend_l = 0, poly_k = 0, poly_l = 0, spiky_k = 0, spiky_l = 0;
     std::vector<Real> lutW, lutG;
     // fluid
     Real density0 = 1000, V = 0;
@@ -147,9 +148,81 @@ V3 avxGradW(V3 r)
     res = rl > static_cast<Real>(1.0e-9) ? res : static_cast<Real>(0.0);
     return { r.x * res, r.y * res, r.z * res };
 }
-// sim->W / sim->gradW: the configured scalar kernel (Simulation.h:381-382)
-Real simW(V3 r) { return g->kernel == 4 ? lutWf(r) : cubicW(std::sqrt(dot(r, r))); }
-V3 simGradW(V3 r) { return g->kernel == 4 ? lutGradW(r) : cubicGradW(r); }
+// WendlandQuinticC2Kernel (SPHKernels.h:291-320)
+Real wendlandW(Real r)
+{
+    Real res = 0.0;
+    const Real q = r / g->support;
+    if (q <= 1.0) res = g->wend_k * std::pow(static_cast<Real>(1.0) - q, static_cast<Real>(4.0)) * (static_cast<Real>(4.0) * q + static_cast<Real>(1.0));
+    return res;
+}
+V3 wendlandGradW(V3 r)
+{
+    V3 res = { 0, 0, 0 };
+    const Real rl = std::sqrt(dot(r, r));
+    const Real q = rl / g->support;
+    if (q <= 1.0) {
+        const Real f = static_cast<Real>(1.0) / (rl * g->support);
+        const Real s = g->wend_l * q * std::pow(static_cast<Real>(1.0) - q, static_cast<Real>(3.0));
+        res = { s * (r.x * f), s * (r.y * f), s * (r.z * f) };
+    }
+    return res;
+}
+// Poly6Kernel (SPHKernels.h:138-167)
+Real poly6W(V3 r)
+{
+    Real res = 0.0;
+    const Real r2 = dot(r, r), radius2 = g->support * g->support;
+    if (r2 <= radius2) res = std::pow(radius2 - r2, static_cast<Real>(3.0)) * g->poly_k;
+    return res;
+}
+V3 poly6GradW(V3 r)
+{
+    V3 res = { 0, 0, 0 };
+    const Real r2 = dot(r, r), radius2 = g->support * g->support;
+    if (r2 <= radius2) { const Real tmp = radius2 - r2; const Real s = g->poly_l * tmp * tmp; res = { s * r.x, s * r.y, s * r.z }; }
+    return res;
+}
+// SpikyKernel (SPHKernels.h:225-257)
+Real spikyW(V3 r)
+{
+    Real res = 0.0;
+    const Real r2 = dot(r, r), radius2 = g->support * g->support;
+    if (r2 <= radius2) res = g->spiky_k * std::pow(g->support - std::sqrt(r2), static_cast<Real>(3.0));
+    return res;
+}
+V3 spikyGradW(V3 r)
+{
+    V3 res = { 0, 0, 0 };
+    const Real r2 = dot(r, r), radius2 = g->support * g->support;
+    if (r2 <= radius2) {
+        const Real r_l = std::sqrt(r2), hr = g->support - r_l;
+        const Real s = g->spiky_l * (hr * hr), f = static_cast<Real>(1.0) / r_l;
+        res = { s * r.x * f, s * r.y * f, s * r.z * f };
+    }
+    return res;
+}
+// sim->W / sim->gradW: the configured scalar kernels (Simulation.h:381-382; setKernel / setGradKernel, Simulation.cpp:306-393)
+Real simW(V3 r)
+{
+    switch (g->kernel) {
+        case 1: return wendlandW(std::sqrt(dot(r, r)));
+        case 2: return poly6W(r);
+        case 3: return spikyW(r);
+        case 4: return lutWf(r);
+        default: return cubicW(std::sqrt(dot(r, r)));
+    }
+}
+V3 simGradW(V3 r)
+{
+    switch (g->gradKernel) {
+        case 1: return wendlandGradW(r);
+        case 2: return poly6GradW(r);
+        case 3: return spikyGradW(r);
+        case 4: return lutGradW(r);
+        default: return cubicGradW(r);
+    }
+}
 // kernel used inside the solver sums
 Real solverW(V3 r) { return ORACLE_AVX_VARIANT ? avxW(r) : simW(r); }
 V3 solverGradW(V3 r) { return ORACLE_AVX_VARIANT ? avxGradW(r) : simGradW(r); }
@@ -170,7 +243,18 @@ void initKernels()
     g->l = static_cast<Real>(48.0) / (pi * h3);
 #endif
     g->invR2 = g->invR * g->invR;
-    g->W_zero = cubicW(0);
+    {   // setRadius of the other kernels (SPHKernels.h:107-118, 196-204, 268-277)
+        const Real h6 = std::pow(g->support, static_cast<Real>(6.0)), h9 = std::pow(g->support, static_cast<Real>(9.0));
+        g->wend_k = static_cast<Real>(21.0) / (static_cast<Real>(2.0) * pi * h3);
+        g->wend_l = -static_cast<Real>(210.0) / (pi * h3);
+        g->poly_k = static_cast<Real>(315.0) / (static_cast<Real>(64.0) * pi * h9);
+        g->poly_l = -static_cast<Real>(945.0) / (static_cast<Real>(32.0) * pi * h9);
+        g->spiky_k = static_cast<Real>(15.0) / (pi * h6);
+        g->spiky_l = -static_cast<Real>(45.0) / (pi * h6);
+    }
+    // sim->W_zero() of the configured kernel; the AVX solver sums use CubicKernel_AVX::W_zero() regardless (TimeStep.cpp:70)
+    g->simW_zero = g->kernel == 1 ? wendlandW(0) : g->kernel == 2 ? poly6W({ 0, 0, 0 }) : g->kernel == 3 ? spikyW({ 0, 0, 0 }) : cubicW(0);
+    g->W_zero = ORACLE_AVX_VARIANT ? cubicW(0) : g->simW_zero;
     g->lutW.resize(LUT_RES);
     g->lutG.resize(LUT_RES + 1);
     const Real stepSize = g->support / (Real)(LUT_RES - 1);
@@ -286,7 +370,7 @@ void computeBoundaryVolume()
     g->bV.resize(g->bx.size());
     #pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)g->bx.size(); ++i) {
-        Real delta = g->W_zero;
+        Real delta = g->simW_zero;
         for (unsigned long long k = off[i]; k < off[i + 1]; ++k) delta += simW(g->bx[i] - g->bx[nb[k]]);
         g->bV[i] = static_cast<Real>(1.0) / delta;
     }
@@ -610,7 +694,13 @@ int ref_add_fluid(const Real* x, const Real* v, unsigned n, double density0)
     return 0;
 }
 
-int ref_configure(int kernel, int) { g->kernel = kernel; return 0; }
+int ref_configure(int kernel, int gradKernel)
+{
+    g->kernel = (kernel < 0 || kernel > 4) ? 0 : kernel;                 // Simulation.cpp:346-347
+    g->gradKernel = (gradKernel < 0 || gradKernel > 4) ? 0 : gradKernel; // Simulation.cpp:312-313
+    initKernels();   // W_zero follows the configured kernel
+    return 0;
+}
 
 int ref_add_boundary(const Real* x, unsigned n)
 {
@@ -681,7 +771,7 @@ double ref_time() { return g->time; }
 double ref_time_step_size() { return g->h; }
 int ref_iterations() { return (int)g->iterations; }
 int ref_iterations_v() { return (int)g->iterationsV; }
-double ref_w_zero() { return g->W_zero; }
+double ref_w_zero() { return g->simW_zero; }
 double ref_fluid_volume(int) { return g->V; }
 int ref_kernel() { return g->kernel; }
 

@@ -17,5 +17,5 @@ def port_available(precision: str) -> bool:
     return os.path.exists(port_lib_path(precision))
 
 
-def build_port_scene(scene, precision="f64", kernel=4, **params) -> RefSim:
-    return build_ref_scene(scene, precision, kernel=kernel, lib_path=port_lib_path(precision), **params)
+def build_port_scene(scene, precision="f64", kernel=4, grad_kernel=None, **params) -> RefSim:
+    return build_ref_scene(scene, precision, kernel=kernel, lib_path=port_lib_path(precision), grad_kernel=grad_kernel, **params)

@@ -91,10 +91,10 @@ class RefSim:
     def configure(self, kernel=4, grad_kernel=None):
         self.lib.ref_configure(int(kernel), int(kernel if grad_kernel is None else grad_kernel))
 
-    def configure_b200(self, kernel=4, libdir=None):
+    def configure_b200(self, kernel=4, libdir=None, grad_kernel=None):
         """Install the product's C++ drop-in TimeStepDFSPH_B200 as the solver of the reference Simulation."""
         libdir = libdir or os.path.join(os.path.dirname(_HERE), "splishsplash_b200")
-        rc = self.lib.ref_configure_b200(int(kernel), int(kernel), libdir.encode())
+        rc = self.lib.ref_configure_b200(int(kernel), int(kernel if grad_kernel is None else grad_kernel), libdir.encode())
         if rc != 0:
             raise RuntimeError(self.lib.ref_last_error().decode())
 
@@ -231,16 +231,16 @@ class RefSim:
         self.destroy()
 
 
-def build_ref_scene(scene, precision="f64", kernel=4, lib_path=None, b200=False, **params):
+def build_ref_scene(scene, precision="f64", kernel=4, lib_path=None, b200=False, grad_kernel=None, **params):
     """Create a RefSim for a ``splishsplash_b200.scenes`` scene dict.  b200=True swaps the reference's TimeStepDFSPH
     for the drop-in TimeStepDFSPH_B200 (everything else stays the reference's own code)."""
     sim = RefSim(precision, lib_path)
     sim.create(scene["radius"])
     sim.add_fluid(scene["fluid_x"], scene.get("fluid_v"))
     if b200:
-        sim.configure_b200(kernel)
+        sim.configure_b200(kernel, grad_kernel=grad_kernel)
     else:
-        sim.configure(kernel)
+        sim.configure(kernel, grad_kernel)
     if scene.get("boundary_x") is not None and len(scene["boundary_x"]):
         sim.add_boundary(scene["boundary_x"])
     if params:

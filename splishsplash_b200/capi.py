@@ -13,7 +13,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_COMM = -1, -2, -3, -4, -5
-KERNEL_CUBIC, KERNEL_PRECOMPUTED_CUBIC = 0, 4
+KERNEL_CUBIC, KERNEL_WENDLAND_QUINTIC_C2, KERNEL_POLY6, KERNEL_SPIKY, KERNEL_PRECOMPUTED_CUBIC = 0, 1, 2, 3, 4
 
 # dfsph_b200_field
 FIELD_POSITION, FIELD_VELOCITY, FIELD_DENSITY, FIELD_FACTOR, FIELD_DENSITY_ADV = 0, 1, 2, 3, 4
@@ -34,7 +34,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("kernel", C.c_int32), ("particle_radius", C.c_double),
                 ("max_fluid_particles", C.c_uint64), ("max_fluid_neighbors", C.c_int32),
                 ("max_boundary_neighbors", C.c_int32), ("domain_min", C.c_double * 3), ("domain_max", C.c_double * 3),
-                ("rank", C.c_int32), ("world_size", C.c_int32)]
+                ("rank", C.c_int32), ("world_size", C.c_int32), ("grad_kernel", C.c_int32)]
 
 
 class Params(C.Structure):

@@ -109,7 +109,7 @@ __host__ __device__ __forceinline__ int cell_coord_fine(Real x, double o, double
 // ---------------------------------------------------------------------------------------------------------------
 // SPH constants (host-computed in Real exactly as the reference's setRadius functions do).
 // ---------------------------------------------------------------------------------------------------------------
-enum KernelMode { KM_CUBIC_AVX = 0, KM_CUBIC = 1, KM_LUT = 2 };
+enum KernelMode { KM_CUBIC_AVX = 0, KM_CUBIC = 1, KM_LUT = 2, KM_GENERIC = 3 };   // GENERIC: any kernel/gradKernel pair, chosen at run time
 
 struct SphConst {
     Real R;            // support radius (4 r)
@@ -124,6 +124,11 @@ struct SphConst {
     const Real* lutW;      // [9999]  pre-averaged: 0.5*(m_W[i] + m_W[i+1]), the exact value the reference computes per call
     const Real* lutGradW;  // [9999]  pre-averaged: 0.5*(m_gradW[i] + m_gradW[i+1])
     int mode;          // KernelMode used by the solver sums
+    // KM_GENERIC (next-row f2): Simulation "kernel" / "gradKernel" ids 0 cubic, 1 Wendland quintic C2, 2 Poly6, 3 Spiky,
+    // 4 precomputed cubic (Simulation.cpp:306-393) and the m_k / m_l constants of kernels 1..3 (SPHKernels.h:107-118,
+    // 196-204, 268-277)
+    int w_kind, g_kind;
+    Real gen_k[4], gen_l[4];
 };
 
 // Solver control block, resident in device memory so that no host round trip is needed inside a step.

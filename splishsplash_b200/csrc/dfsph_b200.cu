@@ -248,17 +248,37 @@ static int setup_constants(dfsph_b200_ctx* c)
     s.lutW = c->lutW;
     s.lutGradW = c->lutGradW;
 
-    const bool lut = (c->cfg.kernel == DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC);
+    // constants of the other selectable kernels, computed in Real as their setRadius does (next-row f2)
+    {
+        const Real h9 = std::pow(radius, static_cast<Real>(9.0)), h6 = std::pow(radius, static_cast<Real>(6.0));
+        s.gen_k[0] = s.k; s.gen_l[0] = s.l;
+        s.gen_k[1] = static_cast<Real>(21.0) / (static_cast<Real>(2.0) * pi * h3);    // SPHKernels.h:286-287
+        s.gen_l[1] = -static_cast<Real>(210.0) / (pi * h3);
+        s.gen_k[2] = static_cast<Real>(315.0) / (static_cast<Real>(64.0) * pi * h9);  // SPHKernels.h:112-113
+        s.gen_l[2] = -static_cast<Real>(945.0) / (static_cast<Real>(32.0) * pi * h9);
+        s.gen_k[3] = static_cast<Real>(15.0) / (pi * h6);                              // SPHKernels.h:209-210
+        s.gen_l[3] = -static_cast<Real>(45.0) / (pi * h6);
+    }
+    const int wk = c->cfg.kernel, gk = c->cfg.grad_kernel < 0 ? c->cfg.kernel : c->cfg.grad_kernel;
+    s.w_kind = wk; s.g_kind = gk;
+    const int scalar_mode = (wk == 4 && gk == 4) ? KM_LUT : (wk == 0 && gk == 0) ? KM_CUBIC : KM_GENERIC;
+    // W(0) of the configured kernel (Simulation::setKernel, Simulation.cpp:338-393)
+    Real w_zero = s.W_zero;
+    if (wk == 1) w_zero = s.gen_k[1];
+    else if (wk == 2) w_zero = std::pow(radius * radius, static_cast<Real>(3.0)) * s.gen_k[2];
+    else if (wk == 3) w_zero = s.gen_k[3] * std::pow(radius, static_cast<Real>(3.0));
 #if DFSPH_REAL_IS_DOUBLE
-    c->solver_mode = lut ? KM_LUT : KM_CUBIC;
+    c->solver_mode = scalar_mode;
+    s.W_zero = w_zero;
 #else
     c->solver_mode = KM_CUBIC_AVX;   // the AVX solver ignores the kernel setting
 #endif
-    c->bv_mode = lut ? KM_LUT : KM_CUBIC;
+    c->bv_mode = scalar_mode;
     s.mode = c->solver_mode;
     c->sph = s;
     c->sph_bv = s;
     c->sph_bv.mode = c->bv_mode;
+    c->sph_bv.W_zero = w_zero;
     return 0;
 }
 
@@ -287,6 +307,7 @@ void dfsph_b200_default_config(dfsph_b200_config* cfg)
     memset(cfg, 0, sizeof(*cfg));
     cfg->device = 0;
     cfg->kernel = DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC;
+    cfg->grad_kernel = -1;
     cfg->particle_radius = 0.025;
     cfg->max_fluid_neighbors = 64;
     cfg->max_boundary_neighbors = 64;
@@ -319,8 +340,8 @@ int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out)
 {
     if (!cfg || !out) { g_create_error = "null argument"; return DFSPH_B200_ERR_INVALID; }
     *out = nullptr;
-    if (cfg->kernel != DFSPH_B200_KERNEL_CUBIC && cfg->kernel != DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC) {
-        g_create_error = "unsupported kernel (0 = cubic, 4 = precomputed cubic)";
+    if (cfg->kernel < 0 || cfg->kernel > 4 || cfg->grad_kernel < -1 || cfg->grad_kernel > 4) {
+        g_create_error = "unsupported kernel (0 cubic, 1 Wendland quintic C2, 2 Poly6, 3 Spiky, 4 precomputed cubic; grad_kernel -1 = same as kernel)";
         return DFSPH_B200_ERR_UNSUPPORTED;
     }
     if (!(cfg->particle_radius > 0.0)) { g_create_error = "particle_radius must be > 0"; return DFSPH_B200_ERR_INVALID; }
@@ -783,6 +804,7 @@ int dfsph_b200_compute_boundary_volume(dfsph_b200_ctx* c)
     CUDA_TRY(c, cudaMalloc((void**)&vol, (size_t)nb * sizeof(Real)));
     const Real W0 = c->sph_bv.W_zero;   // sim->W_zero() (BoundaryModel_Akinci2012.cpp:61)
     if (c->bv_mode == KM_LUT) k_boundary_volume<KM_LUT><<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->grid, c->sph_bv, W0, c->bpos, c->bcell_start, vol);
+    else if (c->bv_mode == KM_GENERIC) k_boundary_volume<KM_GENERIC><<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->grid, c->sph_bv, W0, c->bpos, c->bcell_start, vol);
     else k_boundary_volume<KM_CUBIC><<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->grid, c->sph_bv, W0, c->bpos, c->bcell_start, vol);
     k_set_w<<<div_up(nb, 256), 256, 0, c->stream>>>(c->bpos, vol, nb);
     cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -1264,6 +1286,7 @@ static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
     CUDA_TRY(c, cudaEventRecord(c->ev[1], st));
 #if DFSPH_REAL_IS_DOUBLE
     if (c->solver_mode == KM_CUBIC) rc = run_solver<KM_CUBIC>(c);
+    else if (c->solver_mode == KM_GENERIC) rc = run_solver<KM_GENERIC>(c);
     else rc = run_solver<KM_LUT>(c);
 #else
     rc = run_solver<KM_CUBIC_AVX>(c);
@@ -1316,6 +1339,7 @@ int dfsph_b200_search_and_density(dfsph_b200_ctx* c)
     // density only: run the fused sweep without the divergence part (factor is a by-product)
 #if DFSPH_REAL_IS_DOUBLE
     if (c->solver_mode == KM_CUBIC) k_init_sweep<KM_CUBIC, false><<<grid, DFSPH_BLOCK, 0, c->stream>>>(f, c->sph, c->bpos, c->ctrl);
+    else if (c->solver_mode == KM_GENERIC) k_init_sweep<KM_GENERIC, false><<<grid, DFSPH_BLOCK, 0, c->stream>>>(f, c->sph, c->bpos, c->ctrl);
     else k_init_sweep<KM_LUT, false><<<grid, DFSPH_BLOCK, 0, c->stream>>>(f, c->sph, c->bpos, c->ctrl);
 #else
     k_init_sweep<KM_CUBIC_AVX, false><<<grid, DFSPH_BLOCK, 0, c->stream>>>(f, c->sph, c->bpos, c->ctrl);
@@ -1524,7 +1548,8 @@ __global__ void k_eval_kernel(SphConst c, unsigned n, const Real* __restrict__ r
 
 extern "C" {
 
-// kernel: 0 cubic (scalar arithmetic), 4 precomputed cubic, -1 = the solver's own kernel (CubicKernel_AVX in f32)
+// kernel: 0 cubic (scalar arithmetic), 1 Wendland quintic C2, 2 Poly6, 3 Spiky, 4 precomputed cubic,
+// -1 = the solver's own kernel (CubicKernel_AVX in f32; the configured kernel / gradKernel pair in f64)
 int dfsph_b200_eval_kernel(dfsph_b200_ctx* c, int kernel, uint64_t n64, const void* r, void* W, void* gradW)
 {
     CHECK_CTX(c);
@@ -1538,7 +1563,10 @@ int dfsph_b200_eval_kernel(dfsph_b200_ctx* c, int kernel, uint64_t n64, const vo
     if (kernel == DFSPH_B200_KERNEL_CUBIC) mode = KM_CUBIC;
     else if (kernel == DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC) mode = KM_LUT;
     else if (kernel == -1) mode = c->solver_mode;
+    else if (kernel >= 1 && kernel <= 3) mode = KM_GENERIC;
     else CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "unsupported kernel id %d", kernel);
+    SphConst sc = c->sph;
+    if (kernel >= 1 && kernel <= 3) { sc.w_kind = kernel; sc.g_kind = kernel; }
     const unsigned n = (unsigned)n64;
     if (n == 0) return DFSPH_B200_OK;
     Real *dr = nullptr, *dW = nullptr, *dG = nullptr;
@@ -1548,9 +1576,10 @@ int dfsph_b200_eval_kernel(dfsph_b200_ctx* c, int kernel, uint64_t n64, const vo
     if (e == cudaSuccess) e = cudaMemcpy(dr, r, (size_t)n * 3 * sizeof(Real), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         const unsigned g = div_up(n, 256);
-        if (mode == KM_CUBIC_AVX) k_eval_kernel<KM_CUBIC_AVX><<<g, 256, 0, c->stream>>>(c->sph, n, dr, dW, dG);
-        else if (mode == KM_CUBIC) k_eval_kernel<KM_CUBIC><<<g, 256, 0, c->stream>>>(c->sph, n, dr, dW, dG);
-        else k_eval_kernel<KM_LUT><<<g, 256, 0, c->stream>>>(c->sph, n, dr, dW, dG);
+        if (mode == KM_CUBIC_AVX) k_eval_kernel<KM_CUBIC_AVX><<<g, 256, 0, c->stream>>>(sc, n, dr, dW, dG);
+        else if (mode == KM_CUBIC) k_eval_kernel<KM_CUBIC><<<g, 256, 0, c->stream>>>(sc, n, dr, dW, dG);
+        else if (mode == KM_GENERIC) k_eval_kernel<KM_GENERIC><<<g, 256, 0, c->stream>>>(sc, n, dr, dW, dG);
+        else k_eval_kernel<KM_LUT><<<g, 256, 0, c->stream>>>(sc, n, dr, dW, dG);
         e = cudaStreamSynchronize(c->stream);
     }
     if (e == cudaSuccess && W) e = cudaMemcpy(W, dW, (size_t)n * sizeof(Real), cudaMemcpyDeviceToHost);

@@ -244,7 +244,8 @@ void TimeStepDFSPH_B200::uploadModel()
 	dfsph_b200_config cfg;
 	m_api->default_config(&cfg);
 	cfg.particle_radius = sim->getParticleRadius();
-	cfg.kernel = sim->getKernel();      // 0 cubic / 4 precomputed cubic (Simulation.cpp:215-253)
+	cfg.kernel = sim->getKernel();          // "kernel" / "gradKernel" enum ids (Simulation.cpp:215-253)
+	cfg.grad_kernel = sim->getGradKernel();
 	if (const char* dev = std::getenv("DFSPH_B200_DEVICE")) cfg.device = std::atoi(dev);
 	check(m_api->create(&cfg, &m_ctx), "dfsph_b200_create");
 	pushParameters();

@@ -33,7 +33,7 @@ class TimeStepDFSPH_B200:
     METHOD_NAME = "DFSPH_B200"
 
     def __init__(self, precision="f32", particle_radius=0.025, kernel=capi.KERNEL_PRECOMPUTED_CUBIC, device=0,
-                 max_fluid_neighbors=64, max_boundary_neighbors=64, max_fluid_particles=0, domain=None):
+                 max_fluid_neighbors=64, max_boundary_neighbors=64, max_fluid_particles=0, domain=None, grad_kernel=None):
         self.precision = precision
         self.dtype = np.float32 if precision == "f32" else np.float64
         self.lib = capi.load(precision)
@@ -41,6 +41,7 @@ class TimeStepDFSPH_B200:
         self.lib.dfsph_b200_default_config(C.byref(cfg))
         cfg.device = device
         cfg.kernel = kernel
+        cfg.grad_kernel = -1 if grad_kernel is None else grad_kernel   # Simulation "gradKernel"; default: same as "kernel"
         cfg.particle_radius = particle_radius
         cfg.max_fluid_neighbors = max_fluid_neighbors
         cfg.max_boundary_neighbors = max_boundary_neighbors
@@ -269,10 +270,11 @@ class TimeStepDFSPH_B200:
         return W, g
 
 
-def build_b200_scene(scene, precision="f32", kernel=capi.KERNEL_PRECOMPUTED_CUBIC, boundary_V=None, device=0, **params):
+def build_b200_scene(scene, precision="f32", kernel=capi.KERNEL_PRECOMPUTED_CUBIC, boundary_V=None, device=0, grad_kernel=None,
+                     **params):
     """Create a TimeStepDFSPH_B200 for a ``splishsplash_b200.scenes`` scene dict (same call order as the reference
     harness oracle/refsim.build_ref_scene)."""
-    ts = TimeStepDFSPH_B200(precision, scene["radius"], kernel, device=device)
+    ts = TimeStepDFSPH_B200(precision, scene["radius"], kernel, device=device, grad_kernel=grad_kernel)
     if params:
         ts.set(**params)
     ts.set_fluid(scene["fluid_x"], scene.get("fluid_v"))

@@ -30,6 +30,9 @@ FIXTURES = [  # name, scene factory, precision, kernel, steps, params
      dict(viscosityMethod=1, viscosity=0.05, viscosityBoundary=0.02)),   # next-row f1: Viscosity_Standard
     ("dambreak_tiny_visc_f32_k4", lambda dt: _sheared(scenes.dam_break("tiny", dtype=dt)), "f32", 4, 3,
      dict(viscosityMethod=1, viscosity=0.05, viscosityBoundary=0.0)),
+    # next-row f2: the other selectable kernels of the scalar (double) build; "gradKernel" is popped from the params
+    ("dambreak_tiny_f64_k1", lambda dt: scenes.dam_break("tiny", dtype=dt), "f64", 1, 2, {}),              # Wendland quintic C2
+    ("dambreak_tiny_f64_k2g3", lambda dt: scenes.dam_break("tiny", dtype=dt), "f64", 2, 2, dict(gradKernel=3)),   # Poly6 / Spiky
 ]
 
 
@@ -41,13 +44,18 @@ def _sheared(sc):
 
 
 def main():
+    only = set(sys.argv[1:])   # optional: names of the fixtures to (re)generate
     for name, factory, prec, kernel, steps, params in FIXTURES:
+        if only and name not in only:
+            continue
         dt = np.float32 if prec == "f32" else np.float64
         sc = factory(dt)
-        sim = refsim.build_ref_scene(sc, prec, kernel=kernel, **params)
+        params = dict(params)
+        grad_kernel = int(params.pop("gradKernel", kernel))
+        sim = refsim.build_ref_scene(sc, prec, kernel=kernel, grad_kernel=grad_kernel, **params)
         out = {"fluid_x": sc["fluid_x"], "boundary_x": sc["boundary_x"], "radius": np.float64(sc["radius"]),
                **({"fluid_v": sc["fluid_v"]} if sc.get("fluid_v") is not None else {}),
-               "kernel": np.int32(kernel), "steps": np.int32(steps)}
+               "kernel": np.int32(kernel), "grad_kernel": np.int32(grad_kernel), "steps": np.int32(steps)}
         for k, v in params.items():
             out["param_" + k] = np.float64(v)
         bx, bV = sim.boundary(0)

@@ -28,13 +28,13 @@ def dtype_of(precision):
     return np.float32 if precision == "f32" else np.float64
 
 
-def make_oracle(scene, precision, kernel=4, **params):
+def make_oracle(scene, precision, kernel=4, grad_kernel=None, **params):
     """Reference-side simulation: the reference's own sources if oracle/_ref is built, else the C++ restatement."""
     from oracle import refsim
     if refsim.ref_available(precision):
-        return refsim.build_ref_scene(scene, precision, kernel=kernel, **params), "reference"
+        return refsim.build_ref_scene(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params), "reference"
     from oracle import portsim
-    return portsim.build_port_scene(scene, precision, kernel=kernel, **params), "port"
+    return portsim.build_port_scene(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params), "port"
 
 
 def scaled_err(a, b):
@@ -93,12 +93,12 @@ def sync_state(ref, dev):
     dev.setValue("timeStepSize", ref.h)
 
 
-def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, check_neighbors=True, **params):
+def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, check_neighbors=True, grad_kernel=None, **params):
     """Run `steps` steps on the oracle and on the device from identical input states; compare every per-step field,
     the iteration counts, the new time step size and (first step) the neighbour sets.  Returns a result dict."""
     from splishsplash_b200.solver import build_b200_scene
     tol = TOL[precision] if tol is None else tol
-    ref, kind = make_oracle(scene, precision, kernel=kernel, **params)
+    ref, kind = make_oracle(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params)
     res = {"ok": True, "oracle": kind, "precision": precision, "steps": [], "max_err": {}}
     try:
         bx, bV = (None, None)
@@ -106,7 +106,7 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
             bx, bV = ref.boundary(0)
         # boundary volumes: device-computed, checked against the reference's (then the reference's are used so that
         # the step comparison starts from identical inputs)
-        dev = build_b200_scene(scene, precision, kernel=kernel, **params)
+        dev = build_b200_scene(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params)
         try:
             if bx is not None:
                 # the reference z-sorts its boundary arrays once; match particles by position

@@ -40,7 +40,7 @@ def test_defaults_match_reference_defaults():
     assert list(p.gravitation) == [0.0, -9.81, 0.0]
     c = capi.Config()
     lib.dfsph_b200_default_config(C.byref(c))
-    assert c.kernel == capi.KERNEL_PRECOMPUTED_CUBIC and c.particle_radius == 0.025
+    assert c.kernel == capi.KERNEL_PRECOMPUTED_CUBIC and c.grad_kernel == -1 and c.particle_radius == 0.025
 
 
 def test_no_cpu_fallback():
@@ -59,7 +59,7 @@ def test_create_rejects_bad_arguments():
     c = capi.Config()
     lib.dfsph_b200_default_config(C.byref(c))
     ctx = C.c_void_p()
-    c.kernel = 2   # Poly6: not a DFSPH kernel on this path
+    c.kernel = 5   # ids 5, 6 are the 2-D kernels: not on this path
     assert lib.dfsph_b200_create(C.byref(c), C.byref(ctx)) == capi.ERR_UNSUPPORTED
     c.kernel = 4
     c.particle_radius = 0.0

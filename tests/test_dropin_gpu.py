@@ -12,8 +12,8 @@ from tests.parity import TOL, conditioned_errors, dtype_of, scaled_err
 pytestmark = pytest.mark.gpu
 
 
-def _run(scene, prec, b200, steps):
-    sim = refsim.build_ref_scene(scene, prec, kernel=4, b200=b200)
+def _run(scene, prec, b200, steps, kernel=4, grad=4):
+    sim = refsim.build_ref_scene(scene, prec, kernel=kernel, grad_kernel=grad, b200=b200)
     out = []
     try:
         name = sim.method_name
@@ -27,14 +27,14 @@ def _run(scene, prec, b200, steps):
     return name, out
 
 
-@pytest.mark.parametrize("prec", ["f32", "f64"])
-def test_reference_stack_with_b200_solver(prec):
+@pytest.mark.parametrize("prec,kernel,grad", [("f32", 4, 4), ("f64", 4, 4), ("f64", 1, 1), ("f64", 2, 3)])
+def test_reference_stack_with_b200_solver(prec, kernel, grad):
     if not refsim.ref_available(prec):
         pytest.skip("oracle/_ref not present")
     sc = scenes.dam_break("small", dtype=dtype_of(prec))
     steps = 4   # free-running from the same initial state; short enough that rounding differences stay below tolerance
-    name_ref, ref = _run(sc, prec, False, steps)
-    name_dev, dev = _run(sc, prec, True, steps)
+    name_ref, ref = _run(sc, prec, False, steps, kernel, grad)
+    name_dev, dev = _run(sc, prec, True, steps, kernel, grad)
     assert name_ref == "DFSPH" and name_dev == "DFSPH_B200"
     tol = TOL[prec] * (1 if prec == "f64" else 4)   # float: four free-running steps accumulate rounding differences
     for s in range(steps):

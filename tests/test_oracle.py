@@ -29,6 +29,10 @@ def _params_from(g):
     return {k[len("param_"):]: float(g[k]) for k in g.files if k.startswith("param_")}
 
 
+def _grad_kernel(g):
+    return int(g["grad_kernel"]) if "grad_kernel" in g.files else int(g["kernel"])
+
+
 def _prec(path):
     return "f32" if "_f32_" in os.path.basename(path) else "f64"
 
@@ -40,7 +44,7 @@ def test_port_matches_golden(path):
         pytest.skip("liboracle not built (run __graft_entry__.build())")
     g = np.load(path)
     tol = TOL[prec]
-    sim = portsim.build_port_scene(_scene_from(g), prec, kernel=int(g["kernel"]), **_params_from(g))
+    sim = portsim.build_port_scene(_scene_from(g), prec, kernel=int(g["kernel"]), grad_kernel=_grad_kernel(g), **_params_from(g))
     try:
         # boundary volumes
         _, V = sim.boundary(0)
@@ -79,14 +83,18 @@ def test_port_matches_golden(path):
         sim.destroy()
 
 
-@pytest.mark.parametrize("prec,kernel", [("f64", 4), ("f64", 0), ("f32", 4)])
-def test_port_matches_reference_live(prec, kernel):
+@pytest.mark.parametrize("prec,kernel,grad", [("f64", 4, 4), ("f64", 0, 0), ("f32", 4, 4), ("f64", 1, 1), ("f64", 2, 3), ("f64", 3, 2),
+                                              ("f64", 4, 0), ("f32", 1, 1)])
+def test_port_matches_reference_live(prec, kernel, grad):
     if not (refsim.ref_available(prec) and portsim.port_available(prec)):
         pytest.skip("oracle/_ref not present")
     dt = np.float32 if prec == "f32" else np.float64
     sc = scenes.dam_break("small", dtype=dt)
-    ref = refsim.build_ref_scene(sc, prec, kernel=kernel)
-    port = portsim.build_port_scene(sc, prec, kernel=kernel)
+    ref = refsim.build_ref_scene(sc, prec, kernel=kernel, grad_kernel=grad)
+    port = portsim.build_port_scene(sc, prec, kernel=kernel, grad_kernel=grad)
+    by_pos = lambda xv: xv[1][np.lexsort(xv[0].T)]   # (the reference z-sorts its boundary arrays once)
+    assert scaled_err(by_pos(port.boundary(0)), by_pos(ref.boundary(0))) <= TOL[prec]
+    assert abs(port.lib.ref_w_zero() - ref.lib.ref_w_zero()) <= TOL[prec] * abs(ref.lib.ref_w_zero())
     try:
         for s in range(3):
             for f in ("position", "velocity", "p / rho^2", "p_v / rho^2"):

@@ -34,7 +34,8 @@ def test_device_matches_golden(path):
     if "fluid_v" in g.files:
         sc["fluid_v"] = g["fluid_v"]
     params = {k[len("param_"):]: float(g[k]) for k in g.files if k.startswith("param_")}
-    ts = build_b200_scene(sc, prec, kernel=int(g["kernel"]), **params)
+    grad_kernel = int(g["grad_kernel"]) if "grad_kernel" in g.files else None
+    ts = build_b200_scene(sc, prec, kernel=int(g["kernel"]), grad_kernel=grad_kernel, **params)
     try:
         assert scaled_err(ts.boundary_volume(), g["boundary_V"]) <= tol
         did = ts.field("id", by_id=False)
@@ -77,6 +78,16 @@ def test_device_matches_golden(path):
 ])
 def test_step_parity_dam_break(prec, kernel, name, steps):
     r = compare_step(prec, scenes.dam_break(name, dtype=dtype_of(prec)), steps=steps, kernel=kernel)
+    assert r["neighbors_fluid_equal"] and r["neighbors_boundary_equal"], r["summary"]
+    assert r["ok"], r["summary"] + " " + str(r["max_err"])
+
+
+@pytest.mark.parametrize("prec,kernel,grad", [("f64", 1, 1), ("f64", 2, 3), ("f64", 3, 3), ("f64", 4, 0), ("f64", 0, 1), ("f32", 1, 1),
+                                              ("f32", 2, 3)])
+def test_step_parity_other_kernels(prec, kernel, grad):
+    """Next-row f2: every "kernel" / "gradKernel" pair of the 3-D build (Simulation.cpp:306-393).  The double library
+    honours both everywhere; the float library mirrors the AVX build, where they only reach the boundary volumes."""
+    r = compare_step(prec, scenes.dam_break("small", dtype=dtype_of(prec)), steps=4, kernel=kernel, grad_kernel=grad)
     assert r["neighbors_fluid_equal"] and r["neighbors_boundary_equal"], r["summary"]
     assert r["ok"], r["summary"] + " " + str(r["max_err"])
 
@@ -189,7 +200,8 @@ def test_unsupported_and_invalid_calls():
 
 
 # ---- kernel functions: the reference's Tests/Kernel/KernelTests.cpp checks on the device implementations -------------------
-@pytest.mark.parametrize("prec,kernel", [("f32", -1), ("f32", 0), ("f32", 4), ("f64", 0), ("f64", 4)])
+@pytest.mark.parametrize("prec,kernel", [("f32", -1), ("f32", 0), ("f32", 4), ("f64", 0), ("f64", 4), ("f64", 1), ("f64", 2), ("f64", 3),
+                                         ("f32", 1), ("f32", 2), ("f32", 3)])
 def test_kernel_normalisation(prec, kernel):
     """KernelTests.cpp:17-47: sum W V over a 50^3 grid on [-R,R]^3 is 1 (1e-4 float / 1e-5 double), sum gradW V ~ 0,
     W >= 0; R = 0.1."""
