@@ -188,6 +188,8 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's "NCCL version ..." banner off stdout: rank 0 prints ONE JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -317,7 +319,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": dict(cfg, parallelism=("single GPU" if world == 1 else
-                                             f"{world} x-slabs, one per GPU, NCCL ghost exchange (x,v per step; kappa, a per iteration) + migration")),
+                                             f"{world} {'xyz'[sc.get('slab_axis', 2)]}-slabs, one per GPU: migration + ghost x,v per step over NCCL, ghost "
+                                             "kappa / a per iteration and the error all-reduce over NVLink peer memory")),
             "e2e": {"value": n_global * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "warmup": e2e_warm, "ms_per_step": ms_e2e / e2e_steps,
                     "mean_iterations": {"divergence": float(np.mean([i[0] for i in e2e_iters])),
