@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", default="1M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps on one GPU (same window as the device-resident run), 10 on N>1")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (the e2e leg replays the window of the device-resident run)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = one block of --particles per GPU (default); strong = one block of --particles cut into N slabs")
     args = ap.parse_args()
@@ -265,26 +265,26 @@ def main():
             st = ts.step_host(x, v, rho)
             e2e_iters.append((st.iterations_v, st.iterations))
     else:
-        # multi-GPU: the host buffers are in device order (ids are global); upload, step, download
-        n = ts.num_particles          # (migration may have changed the local count)
-        x = ts.pinned((n, 3))
-        v = ts.pinned((n, 3))
-        rho = ts.pinned((n,))
-        x[:] = ts.field("position", by_id=False)
-        v[:] = ts.field("velocity", by_id=False)
-        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else 10
-        e2e_warm = 2
+        # multi-GPU: ids are global, so the host buffers are in this rank's device order (capacity rows); step_host
+        # uploads the owned rows, steps (migration + ghost exchange inside) and downloads the rows owned afterwards.
+        # Same workload, same window: every rank re-submits its initial slab on the same communicator and replays
+        # warm-up + timed steps through step_host.
+        barrier()
+        ts.setValue("timeStepSize", solver_params()["timeStepSize"])
+        ts.set_fluid(sc["fluid_x"], sc.get("fluid_v"), ids=sc["fluid_ids"])
+        n = ts.num_particles
+        cap = ts.capacity
+        x = ts.pinned((cap, 3))
+        v = ts.pinned((cap, 3))
+        rho = ts.pinned((cap,))
+        x[:n] = sc["fluid_x"]
+        v[:n] = sc["fluid_v"] if sc.get("fluid_v") is not None else 0
+        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else args.steps
+        e2e_warm = args.warmup
 
         def e2e_step():
-            m = ts.num_particles
-            ts.set_field("position", x[:m], by_id=False)
-            ts.set_field("velocity", v[:m], by_id=False)
-            st = ts.step(1)
+            st = ts.step_host(x, v, rho)
             e2e_iters.append((st.iterations_v, st.iterations))
-            m2 = min(ts.num_particles, n)
-            x[:m2] = ts.field("position", by_id=False)[:m2]
-            v[:m2] = ts.field("velocity", by_id=False)[:m2]
-            rho[:m2] = ts.field("density", by_id=False)[:m2]
     for _ in range(e2e_warm):
         e2e_step()
     barrier()

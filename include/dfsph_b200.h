@@ -152,7 +152,11 @@ int dfsph_b200_step(dfsph_b200_ctx* ctx, dfsph_b200_step_stats* stats);
 
 /* The same step through HOST buffers, as the reference-facing plugin does when host code touched the particle
  * arrays: uploads x and v (AoS, in id order, i.e. row k = particle with id k), steps, downloads x and v into the
- * same buffers and (if non-NULL) density into `density`.  Copies are inside the call. */
+ * same buffers and (if non-NULL) density into `density`.  Copies are inside the call (the velocity upload overlaps the
+ * neighbour search, the density download overlaps the solver).
+ * Multi-GPU contexts (ids are global): rows are in this rank's device order, the buffers must hold
+ * dfsph_b200_capacity() rows; the first num_particles() rows are read, the first stats->num_particles rows (the count
+ * after this step's migration) are written; DFSPH_B200_FIELD_ID (by_id = 0) names the rows. */
 int dfsph_b200_step_host(dfsph_b200_ctx* ctx, void* x_inout, void* v_inout, void* density_out,
                          dfsph_b200_step_stats* stats);
 
@@ -177,6 +181,7 @@ int dfsph_b200_search_and_density(dfsph_b200_ctx* ctx);
 
 uint64_t dfsph_b200_num_particles(const dfsph_b200_ctx* ctx);
 uint64_t dfsph_b200_num_boundary_particles(const dfsph_b200_ctx* ctx);
+uint64_t dfsph_b200_capacity(const dfsph_b200_ctx* ctx);   /* fluid rows the device arrays (and step_host buffers) hold */
 
 /* Evaluate the device kernel functions W and gradW at n points r (AoS Real[3n]) -> W[n], gradW[3n].
  * Lets the reference's Tests/Kernel/KernelTests.cpp checks run against the device implementations. */

@@ -755,6 +755,12 @@ int dfsph_b200_set_fluid(dfsph_b200_ctx* c, uint64_t n64, const void* x_, const 
     hc.h_step = hc.h;
     hc.multi = c->multi ? 1u : 0u;
     hc.n_global = n;
+    if (c->multi) {
+        // a repeated set_fluid (restart of a run on the same communicator) must not rewind the sequence number of the
+        // peer-memory all-reduce: the peers' tables still hold the values published so far
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaMemcpy(&hc.red_seq, &c->ctrl->red_seq, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    }
     CUDA_TRY(c, cudaMemcpy(c->ctrl, &hc, sizeof(hc), cudaMemcpyHostToDevice));
     c->grid_valid = false;
     c->tables_valid = false;
@@ -1109,7 +1115,7 @@ static int run_solver(dfsph_b200_ctx* c)
     if (c->early_density_host && n > 0) {   // step_host: the density of this step is final here; send it home behind the solver
         CUDA_TRY(c, cudaEventRecord(c->ev_density, st));
         CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_density, 0));
-        k_pack1<Real><<<div_up(n, 256), 256, 0, c->copy_stream>>>(c->density, c->early_density_stage, n, c->id[c->cur]);
+        k_pack1<Real><<<div_up(n, 256), 256, 0, c->copy_stream>>>(c->density, c->early_density_stage, n, multi ? nullptr : c->id[c->cur]);
         CUDA_TRY(c, cudaMemcpyAsync(c->early_density_host, c->early_density_stage, (size_t)n * sizeof(Real), cudaMemcpyDeviceToHost, c->copy_stream));
         c->launches++;
         c->early_density_host = nullptr;
@@ -1426,11 +1432,15 @@ int dfsph_b200_step_host(dfsph_b200_ctx* c, void* x_inout, void* v_inout, void* 
 {
     CHECK_CTX(c);
     cudaSetDevice(c->cfg.device);
-    if (c->multi) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "step_host addresses particles by id; in multi-GPU runs use step + download(by_id=0) with FIELD_ID");
     if (!x_inout || !v_inout) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "x/v buffers are NULL");
+    // single GPU: rows are addressed by particle id (= host array index).  Multi-GPU: ids are global, so rows are in this
+    // rank's device order; the buffers hold dfsph_b200_capacity() rows, the first num_particles() of them are read,
+    // and after the step (migration may have changed the count) the first stats->num_particles rows are written.
+    const bool multi = c->multi;
     const unsigned n = c->n;
+    const unsigned rows = multi ? std::max(c->cap, n) : n;
     const size_t b3 = (size_t)n * 3 * sizeof(Real);
-    { int rc = ensure_stage(c, 2 * b3 + (size_t)n * sizeof(Real)); if (rc) return rc; }
+    { int rc = ensure_stage(c, (size_t)rows * 7 * sizeof(Real)); if (rc) return rc; }
     cudaStream_t st = c->stream;
     if (!c->copy_stream) {
         CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -1439,35 +1449,48 @@ int dfsph_b200_step_host(dfsph_b200_ctx* c, void* x_inout, void* v_inout, void* 
     }
     cudaStream_t cs = c->copy_stream;
     Real* sx = (Real*)c->stage;
-    Real* sv = sx + (size_t)n * 3;
-    Real* sd = sv + (size_t)n * 3;
+    Real* sv = sx + (size_t)rows * 3;
+    Real* sd = sv + (size_t)rows * 3;
     const unsigned g = std::max(div_up(n, 256), 1u);
     if (n > 0) {
-        // x first (the search needs it); v follows on the copy stream and is scattered after the reorder (do_step)
         CUDA_TRY(c, cudaMemcpyAsync(sx, x_inout, b3, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(c, cudaEventRecord(c->ev_copy_in, st));
-        k_unpack3<<<g, 256, 0, st>>>(sx, c->pos[c->cur_pos], n, c->id[c->cur], 0);
+        if (!multi) {
+            // x first (the search needs it); v follows on the copy stream and is scattered after the reorder (do_step)
+            CUDA_TRY(c, cudaEventRecord(c->ev_copy_in, st));
+            k_unpack3<<<g, 256, 0, st>>>(sx, c->pos[c->cur_pos], n, c->id[c->cur], 0);
+            CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_copy_in, 0));   // keep the two uploads back to back on the H2D engine
+            CUDA_TRY(c, cudaMemcpyAsync(sv, v_inout, b3, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(c, cudaEventRecord(c->ev_copy_in, cs));
+            c->late_vel_stage = sv;
+        } else {
+            // the migration of the search packs velocities, so both fields land before the step
+            k_unpack3<<<g, 256, 0, st>>>(sx, c->pos[c->cur_pos], n, nullptr, 0);
+            CUDA_TRY(c, cudaMemcpyAsync(sv, v_inout, b3, cudaMemcpyHostToDevice, st));
+            k_unpack3<<<g, 256, 0, st>>>(sv, c->vel[c->cur], n, nullptr, 0);
+        }
         c->tables_valid = false;
-        CUDA_TRY(c, cudaStreamWaitEvent(cs, c->ev_copy_in, 0));   // keep the two uploads back to back on the H2D engine
-        CUDA_TRY(c, cudaMemcpyAsync(sv, v_inout, b3, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(c, cudaEventRecord(c->ev_copy_in, cs));
-        c->late_vel_stage = sv;
-        if (density_out) { c->early_density_stage = sd; c->early_density_host = density_out; }
     }
+    if (density_out) { c->early_density_stage = sd; c->early_density_host = density_out; }
     int rc = do_step(c, stats);
     c->late_vel_stage = nullptr; c->early_density_host = nullptr;
     if (rc) { cudaStreamSynchronize(cs); return rc; }
-    if (n > 0) {
-        k_pack3<<<g, 256, 0, st>>>(c->pos[c->cur_pos], sx, n, c->id[c->cur]);
-        CUDA_TRY(c, cudaMemcpyAsync(x_inout, sx, b3, cudaMemcpyDeviceToHost, st));
-        k_pack3<<<g, 256, 0, st>>>(c->vel[c->cur], sv, n, c->id[c->cur]);
-        CUDA_TRY(c, cudaMemcpyAsync(v_inout, sv, b3, cudaMemcpyDeviceToHost, st));
-        if (stats) stats->gpu_launches += 3;   // x unpack + two packs (the late v unpack and the density pack are counted in do_step)
+    const unsigned n1 = c->n;   // (multi-GPU: after migration)
+    if (n1 > 0) {
+        const unsigned g1 = div_up(n1, 256);
+        const size_t b31 = (size_t)n1 * 3 * sizeof(Real);
+        const unsigned* idmap = multi ? nullptr : c->id[c->cur];
+        k_pack3<<<g1, 256, 0, st>>>(c->pos[c->cur_pos], sx, n1, idmap);
+        CUDA_TRY(c, cudaMemcpyAsync(x_inout, sx, b31, cudaMemcpyDeviceToHost, st));
+        k_pack3<<<g1, 256, 0, st>>>(c->vel[c->cur], sv, n1, idmap);
+        CUDA_TRY(c, cudaMemcpyAsync(v_inout, sv, b31, cudaMemcpyDeviceToHost, st));
     }
+    if (stats) stats->gpu_launches += (n > 0 ? (multi ? 2u : 1u) : 0u) + (n1 > 0 ? 2u : 0u);   // unpacks + packs issued here
     CUDA_TRY(c, cudaStreamSynchronize(cs));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     return DFSPH_B200_OK;
 }
+
+uint64_t dfsph_b200_capacity(const dfsph_b200_ctx* c) { return c ? c->cap : 0; }
 
 }  // extern "C"
 

@@ -182,7 +182,8 @@ class TimeStepDFSPH_B200:
         return self.stats
 
     def step_host(self, x, v, density=None):
-        """One step through host buffers (x, v in id order; pinned buffers from ``pinned`` recommended)."""
+        """One step through host buffers (x, v in id order; pinned buffers from ``pinned`` recommended).  Multi-GPU: rows in
+        device order, buffers of ``capacity`` rows (see include/dfsph_b200.h)."""
         dp = density.ctypes.data if density is not None else None
         self._check(self.lib.dfsph_b200_step_host(self.ctx, x.ctypes.data, v.ctypes.data, dp, C.byref(self.stats)))
         return self.stats
@@ -221,6 +222,11 @@ class TimeStepDFSPH_B200:
     @property
     def num_particles(self):
         return int(self.lib.dfsph_b200_num_particles(self.ctx))
+
+    @property
+    def capacity(self):
+        """Fluid rows the device arrays hold (size of the step_host buffers in multi-GPU runs)."""
+        return int(self.lib.dfsph_b200_capacity(self.ctx))
 
     @property
     def num_boundary_particles(self):
