@@ -90,6 +90,46 @@ __global__ void __launch_bounds__(256, 8) k_global(const float4* __restrict__ po
     out[i] = make_float4(ax, ay, az, 0.0f);
 }
 
+// variant: S lanes per particle (lane s of a particle takes the list entries k = s mod S), so that the lanes of one
+// request fetch S CONSECUTIVE list entries of 32/S particles (consecutive entries are usually neighbours in memory)
+template <int S>
+__global__ void k_build_split(const unsigned* __restrict__ tab_g, const unsigned* __restrict__ tcnt, unsigned n, unsigned* __restrict__ tab_s,
+                              unsigned* __restrict__ tcnt_s)
+{
+    // re-layout of the S=1 table: tile = 32/S particles; row r of a tile holds entries k = r*S + s of particle p at lane p*S + s
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // particle
+    constexpr unsigned P = 32 / S;
+    const unsigned* tg = tab_g + (size_t)(i >> 5) * K * 32 + (i & 31);
+    unsigned cnt = 0;
+    for (unsigned k = 0; k < tcnt[i >> 5]; ++k) if (tg[(size_t)k * 32] != n) ++cnt;
+    unsigned rows = (cnt + S - 1) / S;
+    // max over the P particles of the tile (P consecutive lanes of this warp)
+    for (unsigned o = 1; o < P; o <<= 1) rows = max(rows, __shfl_xor_sync(0xffffffffu, rows, o));
+    rows = (rows + 3u) & ~3u;
+    unsigned* ts = tab_s + (size_t)(i / P) * K * 32 + (i % P) * S;
+    for (unsigned k = 0; k < rows * S; ++k) ts[(size_t)(k / S) * 32 + (k % S)] = k < cnt ? tg[(size_t)k * 32] : n;
+    if (i % P == 0) tcnt_s[i / P] = rows;
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 8) k_global_split(const float4* __restrict__ pos, const unsigned* __restrict__ tab, const unsigned* __restrict__ tcnt,
+                                                         float4* __restrict__ out)
+{
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;   // lane-slot
+    const unsigned i = t / S;
+    const float4 pi = pos[i];
+    const unsigned m = tcnt[t >> 5];
+    const unsigned* tb = tab + (size_t)(t >> 5) * K * 32 + (t & 31);
+    float ax = 0, ay = 0, az = 0;
+    for (unsigned k = 0; k < m; k += 4) {
+        const unsigned j0 = tb[(size_t)k * 32], j1 = tb[(size_t)(k + 1) * 32], j2 = tb[(size_t)(k + 2) * 32], j3 = tb[(size_t)(k + 3) * 32];
+        const float4 p0 = __ldg(pos + j0), p1 = __ldg(pos + j1), p2 = __ldg(pos + j2), p3 = __ldg(pos + j3);
+        pair(pi, p0, ax, ay, az); pair(pi, p1, ax, ay, az); pair(pi, p2, ax, ay, az); pair(pi, p3, ax, ay, az);
+    }
+    for (unsigned o = 1; o < S; o <<= 1) { ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o); }
+    if (t % S == 0) out[i] = make_float4(ax, ay, az, 0.0f);
+}
+
 // candidate design: CTA = spatial block, halo staged in shared memory, LDS.128 per pair
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_shared(const float4* __restrict__ pos, const unsigned short* __restrict__ tab, const unsigned* __restrict__ tcnt,
@@ -157,6 +197,19 @@ int main()
     timeit("global LDG.128 gathers (current design)", [&] { k_global<<<n / 256, 256>>>(pos, tab_g, tcnt, out_g); });
     timeit("shared-memory tile, 512 threads / block", [&] { k_shared<512><<<n / BP, 512>>>(pos, tab_l, tcnt, out_s, n); });
     timeit("shared-memory tile, 256 threads / block", [&] { k_shared<256><<<n / BP, 256>>>(pos, tab_l, tcnt, out_s, n); });
+    {
+        unsigned *tab_s, *tcnt_s; float4* out_p;
+        CK(cudaMalloc(&tab_s, (size_t)n * K * 4 * 4)); CK(cudaMalloc(&tcnt_s, (size_t)(n / 8) * 4)); CK(cudaMalloc(&out_p, (size_t)n * 16));
+        auto stats = [&](int S) { std::vector<unsigned> c(n / (32 / S)); CK(cudaMemcpy(c.data(), tcnt_s, c.size() * 4, cudaMemcpyDeviceToHost)); double t = 0; for (unsigned v : c) t += v; printf("  S=%d: rows per tile %.1f -> padded slots per particle %.1f\n", S, t / c.size(), t / c.size() * S); };
+        k_build_split<2><<<n / 256, 256>>>(tab_g, tcnt, n, tab_s, tcnt_s); CK(cudaDeviceSynchronize()); stats(2);
+        timeit("global LDG.128, 2 lanes per particle", [&] { k_global_split<2><<<n * 2 / 256, 256>>>(pos, tab_s, tcnt_s, out_p); });
+        k_build_split<4><<<n / 256, 256>>>(tab_g, tcnt, n, tab_s, tcnt_s); CK(cudaDeviceSynchronize()); stats(4);
+        timeit("global LDG.128, 4 lanes per particle", [&] { k_global_split<4><<<n * 4 / 256, 256>>>(pos, tab_s, tcnt_s, out_p); });
+        std::vector<float4> a(n), b(n);
+        CK(cudaMemcpy(a.data(), out_g, (size_t)n * 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), out_p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+        double md = 0, mx = 0; for (unsigned i = 0; i < n; ++i) { md = fmax(md, fabs(a[i].x - b[i].x) + fabs(a[i].y - b[i].y) + fabs(a[i].z - b[i].z)); mx = fmax(mx, fabs(a[i].x)); }
+        printf("  max |S=1 - S=4| = %g (max |a.x| = %g)\n", md, mx);
+    }
     std::vector<float4> a(n), b(n);
     CK(cudaMemcpy(a.data(), out_g, (size_t)n * 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(b.data(), out_s, (size_t)n * 16, cudaMemcpyDeviceToHost));
     double md = 0; for (unsigned i = 0; i < n; ++i) md = fmax(md, fabs(a[i].x - b[i].x) + fabs(a[i].y - b[i].y) + fabs(a[i].z - b[i].z));
