@@ -149,6 +149,21 @@ def run_reference_cpu(sample, precision, steps, warmup, budget_s=25.0):
             "ref_timers_ms": timers}
 
 
+PROGRESS = {"phase": "start", "step": -1}
+
+
+def start_watchdog(seconds, rank):
+    """A hung exchange (a rank spinning on a peer that died) must not hold N GPUs until the caller's limit: after
+    `seconds` the process reports where it was and exits; CUDA tears the context (and any spinning kernel) down."""
+    def run():
+        time.sleep(seconds)
+        sys.stderr.write(f"bench.py watchdog: rank {rank} still in phase '{PROGRESS['phase']}' step {PROGRESS['step']} after "
+                         f"{seconds:.0f} s -- aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=run, daemon=True).start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,8 +203,12 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's "NCCL version ..." banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line on stdout: everything libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        start_watchdog(float(os.environ.get("BENCH_WATCHDOG_S", "420")), rank)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -220,7 +239,9 @@ def main():
         if world > 1:
             dist.barrier()
 
-    for _ in range(args.warmup):
+    PROGRESS["phase"] = "warm-up (device-resident)"
+    for k in range(args.warmup):
+        PROGRESS["step"] = k
         ts.step(1)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -230,7 +251,9 @@ def main():
     launches = 0
     iters = []
     ms_search = ms_solver = 0.0
-    for _ in range(args.steps):
+    PROGRESS["phase"] = "timed steps (device-resident)"
+    for k in range(args.steps):
+        PROGRESS["step"] = k
         st = ts.step(1)
         launches += st.gpu_launches
         iters.append((st.iterations_v, st.iterations))
@@ -269,6 +292,7 @@ def main():
         # uploads the owned rows, steps (migration + ghost exchange inside) and downloads the rows owned afterwards.
         # Same workload, same window: every rank re-submits its initial slab on the same communicator and replays
         # warm-up + timed steps through step_host.
+        PROGRESS["phase"] = "re-submitting the initial slab"
         barrier()
         ts.setValue("timeStepSize", solver_params()["timeStepSize"])
         ts.set_fluid(sc["fluid_x"], sc.get("fluid_v"), ids=sc["fluid_ids"])
@@ -285,13 +309,17 @@ def main():
         def e2e_step():
             st = ts.step_host(x, v, rho)
             e2e_iters.append((st.iterations_v, st.iterations))
-    for _ in range(e2e_warm):
+    PROGRESS["phase"] = "warm-up (host buffers)"
+    for k in range(e2e_warm):
+        PROGRESS["step"] = k
         e2e_step()
     barrier()
     del e2e_iters[:]
     t0 = time.perf_counter()
     ts.timer_start()
-    for _ in range(e2e_steps):
+    PROGRESS["phase"] = "timed steps (host buffers)"
+    for k in range(e2e_steps):
+        PROGRESS["step"] = k
         e2e_step()
     ms_e2e = ts.timer_stop()
     wall_e2e = (time.perf_counter() - t0) * 1000.0
@@ -344,7 +372,8 @@ def main():
                 line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the CPU leg must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    PROGRESS["phase"] = "shutdown"
     ts.close()
     if world > 1:
         dist.destroy_process_group()

@@ -997,12 +997,16 @@ static int run_search(dfsph_b200_ctx* c)
         const unsigned in_l = c->has_left ? c->h_xcnt[1].leave_r : 0u, in_r = c->has_right ? c->h_xcnt[2].leave_l : 0u;
         if (out_l > c->ghost_cap || out_r > c->ghost_cap || in_l + in_r > c->ghost_cap || (unsigned long long)n + in_l + in_r > c->cap)
             CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "migration buffers too small (out %u/%u in %u/%u)", out_l, out_r, in_l, in_r);
-        if (out_l + out_r + in_l + in_r > 0) {
+        // Each exchange is decided PER PAIR of neighbours, from numbers both sides know (my out_l is the left rank's in_r):
+        // a rank-wide test would let an interior rank post messages to a neighbour that has nothing to exchange and
+        // therefore skips the group -- an unmatched send/recv, i.e. a hang (seen at 4 GPUs, never at 2).
+        const bool xl = c->has_left && (out_l + in_l > 0), xr = c->has_right && (out_r + in_r > 0);
+        if (xl || xr) {
             const size_t e = sizeof(Real4), a = sizeof(MigrantAux);
             Real4* pdst = c->pos[c->cur_pos] + n;
             Real4* vdst = c->vel[c->cur] + n;
             NCCL_TRY(c, c->nccl.GroupStart());
-            if (c->has_left) {
+            if (xl) {
                 NCCL_TRY(c, c->nccl.Send(c->send_l, out_l * e, ncclChar, c->rank - 1, c->comm, st));
                 NCCL_TRY(c, c->nccl.Send(c->send_l2, out_l * e, ncclChar, c->rank - 1, c->comm, st));
                 NCCL_TRY(c, c->nccl.Send(c->aux_sl, out_l * a, ncclChar, c->rank - 1, c->comm, st));
@@ -1010,7 +1014,7 @@ static int run_search(dfsph_b200_ctx* c)
                 NCCL_TRY(c, c->nccl.Recv(vdst, in_l * e, ncclChar, c->rank - 1, c->comm, st));
                 NCCL_TRY(c, c->nccl.Recv(c->aux_rl, in_l * a, ncclChar, c->rank - 1, c->comm, st));
             }
-            if (c->has_right) {
+            if (xr) {
                 NCCL_TRY(c, c->nccl.Send(c->send_r, out_r * e, ncclChar, c->rank + 1, c->comm, st));
                 NCCL_TRY(c, c->nccl.Send(c->send_r2, out_r * e, ncclChar, c->rank + 1, c->comm, st));
                 NCCL_TRY(c, c->nccl.Send(c->aux_sr, out_r * a, ncclChar, c->rank + 1, c->comm, st));
