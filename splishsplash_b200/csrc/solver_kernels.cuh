@@ -300,7 +300,7 @@ __device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphCo
 // Single GPU: list == nullptr, skip == nullptr.
 #ifndef DFSPH_ACCEL_MIN_BLOCKS
 #if DFSPH_REAL_IS_DOUBLE
-#define DFSPH_ACCEL_MIN_BLOCKS 1
+#define DFSPH_ACCEL_MIN_BLOCKS (MODE == KM_LUT ? 4 : 1)   /* double, table kernel: 64-register cap (unbounded the compiler takes 92 and halves the occupancy); the analytic kernels need ~80-116 registers */
 #else
 #define DFSPH_ACCEL_MIN_BLOCKS 8    /* 32 registers, full occupancy: -3 % */
 #endif
@@ -391,7 +391,7 @@ __device__ __forceinline__ void solve_control(Ctrl* ctrl, const SolverParams& sp
 // block, which sums partial[0 .. partial_base + gridDim.x) (the export-list launch runs first with finalize = 0).
 #ifndef DFSPH_JACOBI_MIN_BLOCKS
 #if DFSPH_REAL_IS_DOUBLE
-#define DFSPH_JACOBI_MIN_BLOCKS 1   /* the double build needs ~64 registers; forcing more blocks spills */
+#define DFSPH_JACOBI_MIN_BLOCKS (MODE == KM_LUT ? 2 : 1)   /* double, table kernel: 64 registers, 2 x 512 threads per SM (1 block: 104 registers, 35 % slower; 3: spills) */
 #else
 #define DFSPH_JACOBI_MIN_BLOCKS 3   /* 40 registers, 75 % occupancy: 0.97 -> 0.89 ms at 10 M (4 blocks spill: 1.27 ms) */
 #endif
