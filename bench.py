@@ -112,6 +112,10 @@ def solver_params():
 
 def run_reference_cpu(sample, precision, steps, warmup, budget_s=25.0):
     """Time the reference's own CPU DFSPH (oracle/_ref; falls back to the C++ restatement) on `sample` particles."""
+    # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1 to its workers, which would turn
+    # the reference arm at N>1 into a single-thread run
+    host_threads = int(os.environ.get("BENCH_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(host_threads)
     from oracle import refsim, portsim
     from splishsplash_b200 import scenes
     dt = np.float32 if precision == "f32" else np.float64
@@ -124,6 +128,7 @@ def run_reference_cpu(sample, precision, steps, warmup, budget_s=25.0):
         sim = portsim.build_port_scene(sc, precision, kernel=4, **par)
         kind = "port"
     n = sim.num_particles()
+    sim.lib.ref_set_num_threads(host_threads)
     cores = sim.lib.ref_num_threads()
     sim.step(max(warmup, 1))
     sim.reset_step_seconds()
@@ -208,7 +213,7 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
     if world > 1:
-        start_watchdog(float(os.environ.get("BENCH_WATCHDOG_S", "420")), rank)
+        start_watchdog(float(os.environ.get("BENCH_WATCHDOG_S", 300 + 0.5 * (args.steps + args.warmup))), rank)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
