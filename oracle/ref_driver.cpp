@@ -117,6 +117,29 @@ int ref_configure_b200(int kernel, int gradKernel, const char* libdir)
 	g_b200 = true;
 	return 0;
 }
+/* Option B of INTEGRATION.md: the solver is selected like a built-in method, through the "simulationMethod" enum
+   parameter.  Only a library whose Simulation.{h,cpp} carry patches/register_dfsph_b200.patch knows the id (7); the
+   unpatched reference falls back to DFSPH for an unknown id (Simulation.cpp:538-539), reported as -3 here.
+   TimeStepDFSPH_B200's default constructor finds the CUDA library through DFSPH_B200_LIB_DIR. */
+int ref_configure_by_method_id(int method, int kernel, int gradKernel)
+{
+	Simulation* sim = Simulation::getCurrent();
+	sim->setValue<int>(Simulation::BOUNDARY_HANDLING_METHOD, Simulation::ENUM_AKINCI2012);
+	try {
+		sim->setValue<int>(Simulation::SIMULATION_METHOD, method);
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return -2;
+	}
+	if (dynamic_cast<TimeStepDFSPH_B200*>(sim->getTimeStep()) == nullptr) {
+		g_err = "simulationMethod " + std::to_string(method) + " is not DFSPH_B200 in this build (got " + sim->getTimeStep()->getMethodName() + ")";
+		return -3;
+	}
+	sim->setValue<int>(Simulation::KERNEL_METHOD, kernel);
+	sim->setValue<int>(Simulation::GRAD_KERNEL_METHOD, gradKernel);
+	g_b200 = true;
+	return 0;
+}
 const char* ref_last_error() { return g_err.c_str(); }
 
 /* Static Akinci2012 boundary (StaticBoundarySimulator.cpp:146-152 + BoundaryModel_Akinci2012::initModel). */

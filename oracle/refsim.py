@@ -98,6 +98,15 @@ class RefSim:
         if rc != 0:
             raise RuntimeError(self.lib.ref_last_error().decode())
 
+    def configure_by_method_id(self, method=7, kernel=4, grad_kernel=None, libdir=None):
+        """Select the solver through the reference's own "simulationMethod" enum (needs the library built with
+        patches/register_dfsph_b200.patch: oracle/_ref/libsplish_ref_patched_f64.so)."""
+        os.environ["DFSPH_B200_LIB_DIR"] = libdir or os.path.join(os.path.dirname(_HERE), "splishsplash_b200")
+        self.lib.ref_configure_by_method_id.restype = C.c_int
+        rc = self.lib.ref_configure_by_method_id(int(method), int(kernel), int(kernel if grad_kernel is None else grad_kernel))
+        if rc != 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+
     @property
     def method_name(self):
         return self.lib.ref_method_name().decode()
@@ -237,7 +246,9 @@ def build_ref_scene(scene, precision="f64", kernel=4, lib_path=None, b200=False,
     sim = RefSim(precision, lib_path)
     sim.create(scene["radius"])
     sim.add_fluid(scene["fluid_x"], scene.get("fluid_v"))
-    if b200:
+    if b200 == "enum":
+        sim.configure_by_method_id(7, kernel, grad_kernel)
+    elif b200:
         sim.configure_b200(kernel, grad_kernel=grad_kernel)
     else:
         sim.configure(kernel, grad_kernel)

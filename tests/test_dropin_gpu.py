@@ -2,18 +2,23 @@
 TimeManager objects (compiled unmodified into oracle/_ref) run with the product's C++ solver class
 TimeStepDFSPH_B200 (splishsplash_b200/host) installed in place of TimeStepDFSPH, and the result is compared with the
 same stack running the reference's TimeStepDFSPH.  Skipped where oracle/_ref is not present."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import refsim
 from splishsplash_b200 import scenes
-from tests.parity import TOL, conditioned_errors, dtype_of, scaled_err
+from tests.parity import ROOT, TOL, conditioned_errors, dtype_of, scaled_err
 
 pytestmark = pytest.mark.gpu
 
 
-def _run(scene, prec, b200, steps, kernel=4, grad=4):
-    sim = refsim.build_ref_scene(scene, prec, kernel=kernel, grad_kernel=grad, b200=b200)
+PATCHED_F64 = os.path.join(ROOT, "oracle", "_ref", "libsplish_ref_patched_f64.so")
+
+
+def _run(scene, prec, b200, steps, kernel=4, grad=4, lib_path=None):
+    sim = refsim.build_ref_scene(scene, prec, kernel=kernel, grad_kernel=grad, b200=b200, lib_path=lib_path)
     out = []
     try:
         name = sim.method_name
@@ -50,6 +55,23 @@ def test_reference_stack_with_b200_solver(prec, kernel, grad):
             alpha = ref[s]["factor"].astype(np.float64) * h * h
             e = float(np.max(d[alpha > 0] / alpha[alpha > 0]))
         assert e <= tol, (s, "p / rho^2", e)
+
+
+def test_registered_method_id_runs_the_b200_solver():
+    """INTEGRATION.md option B end to end: the reference's Simulation.{h,cpp} with patches/register_dfsph_b200.patch
+    applied (oracle/_ref/libsplish_ref_patched_f64.so) select the drop-in like a built-in method, by
+    "simulationMethod" id 7; the run must match the same stack running the reference's TimeStepDFSPH (id 4)."""
+    if not os.path.exists(PATCHED_F64):
+        pytest.skip("patched reference library not present")
+    prec, steps = "f64", 3
+    sc = scenes.dam_break("small", dtype=dtype_of(prec))
+    name_ref, ref = _run(sc, prec, False, steps, lib_path=PATCHED_F64)
+    name_dev, dev = _run(sc, prec, "enum", steps, lib_path=PATCHED_F64)
+    assert name_ref == "DFSPH" and name_dev == "DFSPH_B200"
+    for s in range(steps):
+        assert ref[s]["iters"] == dev[s]["iters"]
+        for f in ("position", "velocity", "density", "factor", "advected density", "p_v / rho^2"):
+            assert scaled_err(dev[s][f], ref[s][f]) <= TOL[prec], (s, f)
 
 
 def test_neighborhood_search_facade_matches_reference_lists():
