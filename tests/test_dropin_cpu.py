@@ -49,3 +49,24 @@ def test_method_id_7(lib, expect):
                 sim.configure_by_method_id(7, 4)
     finally:
         sim.destroy()
+
+
+def test_pybind_module_of_the_drop_in_imports():
+    """Next-row f4 (pybind half): splishsplash_b200/host/DFSPH_B200Module.cpp, the pySPlisHSPlasH-style module of the
+    drop-in (mirror of pySPlisHSPlasH/DFSPHModule.cpp:50-66), built against the reference stack by oracle/Makefile."""
+    import importlib.util
+    path = os.path.join(ROOT, "oracle", "_ref", "pydfsph_b200_check.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/pydfsph_b200_check.so not present")
+    spec = importlib.util.spec_from_file_location("pydfsph_b200_check", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    cls = m.TimeStepDFSPH_B200
+    assert cls.METHOD_NAME == "DFSPH_B200"
+    ts = cls(os.path.join(ROOT, "splishsplash_b200"))     # loads the CUDA library (no device needed until the first step)
+    assert isinstance(ts, m.TimeStep) and ts.getMethodName() == "DFSPH_B200" and ts.getNumIterations() == 0
+    ts.init()                                              # GenParam registration: the static handles become valid ids
+    handles = [cls.SOLVER_ITERATIONS, cls.MIN_ITERATIONS, cls.MAX_ITERATIONS, cls.MAX_ERROR, cls.SOLVER_ITERATIONS_V,
+               cls.MAX_ITERATIONS_V, cls.MAX_ERROR_V, cls.USE_DIVERGENCE_SOLVER]
+    assert all(h >= 0 for h in handles) and len(set(handles)) == len(handles)
+    ts.setSyncAllFields(False)
