@@ -64,9 +64,16 @@ def test_pybind_module_of_the_drop_in_imports():
     cls = m.TimeStepDFSPH_B200
     assert cls.METHOD_NAME == "DFSPH_B200"
     ts = cls(os.path.join(ROOT, "splishsplash_b200"))     # loads the CUDA library (no device needed until the first step)
-    assert isinstance(ts, m.TimeStep) and ts.getMethodName() == "DFSPH_B200" and ts.getNumIterations() == 0
-    ts.init()                                              # GenParam registration: the static handles become valid ids
-    handles = [cls.SOLVER_ITERATIONS, cls.MIN_ITERATIONS, cls.MAX_ITERATIONS, cls.MAX_ERROR, cls.SOLVER_ITERATIONS_V,
-               cls.MAX_ITERATIONS_V, cls.MAX_ERROR_V, cls.USE_DIVERGENCE_SOLVER]
-    assert all(h >= 0 for h in handles) and len(set(handles)) == len(handles)
-    ts.setSyncAllFields(False)
+    try:
+        assert isinstance(ts, m.TimeStep) and ts.getMethodName() == "DFSPH_B200" and ts.getNumIterations() == 0
+        ts.init()                                          # GenParam registration: the static handles become valid ids
+        handles = [cls.SOLVER_ITERATIONS, cls.MIN_ITERATIONS, cls.MAX_ITERATIONS, cls.MAX_ERROR, cls.SOLVER_ITERATIONS_V,
+                   cls.MAX_ITERATIONS_V, cls.MAX_ERROR_V, cls.USE_DIVERGENCE_SOLVER]
+        assert all(h >= 0 for h in handles) and len(set(handles)) == len(handles)
+        ts.setSyncAllFields(False)
+    finally:
+        # the constructor made Simulation::getCurrent() create a Simulation inside libsplish_ref_f64.so, which the other
+        # tests of this process share: release the solver, then the Simulation
+        del ts
+        import ctypes
+        ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsplish_ref_f64.so")).ref_destroy()
