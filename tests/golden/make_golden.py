@@ -32,6 +32,10 @@ FIXTURES = [  # name, scene factory, precision, kernel, steps, params
      dict(viscosityMethod=1, viscosity=0.05, viscosityBoundary=0.0)),
     # next-row f2: the other selectable kernels of the scalar (double) build; "gradKernel" is popped from the params
     ("dambreak_tiny_f64_k1", lambda dt: scenes.dam_break("tiny", dtype=dt), "f64", 1, 2, {}),              # Wendland quintic C2
+    # edge cases: a coincident pair (|r| = 0: W(0) counted, gradient 0), an isolated particle without any neighbour
+    # (density = V W(0) rho0, factor 0) and one that only sees boundary particles
+    ("edge_tiny_f64_k4", lambda dt: _edge(scenes.dam_break("tiny", dtype=dt)), "f64", 4, 3, {}),
+    ("edge_tiny_f32_k4", lambda dt: _edge(scenes.dam_break("tiny", dtype=dt)), "f32", 4, 3, {}),
     ("dambreak_tiny_f64_k2g3", lambda dt: scenes.dam_break("tiny", dtype=dt), "f64", 2, 2, dict(gradKernel=3)),   # Poly6 / Spiky
 ]
 
@@ -40,6 +44,19 @@ def _sheared(sc):
     v = np.zeros_like(sc["fluid_x"])
     v[:, 0] = 1.5 * np.sin(6.0 * sc["fluid_x"][:, 1])
     sc["fluid_v"] = v
+    return sc
+
+
+def _edge(sc):
+    x = sc["fluid_x"]
+    tmin, tmax = np.asarray(sc["tank_min"]), np.asarray(sc["tank_max"])
+    mid = 0.5 * (tmin + tmax)
+    extra = np.array([
+        x[len(x) // 2],                                              # coincident with an interior particle
+        [mid[0] + 0.31, tmax[1] - 0.333, mid[2]],                    # mid-air, no neighbour at all
+        [tmax[0] - 0.04, tmax[1] - 0.04, tmax[2] - 0.04],            # in a top corner: boundary neighbours only
+    ], dtype=x.dtype)
+    sc["fluid_x"] = np.ascontiguousarray(np.concatenate([x, extra]))
     return sc
 
 
