@@ -333,8 +333,8 @@ def main():
         t = torch.tensor([ms_e2e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
-    h2d = 2 * 3 * R * n
-    d2h = 2 * 3 * R * n + R * n
+    h2d = 2 * 3 * R * n_global            # x, v of every particle of the job, per step (all ranks together)
+    d2h = 2 * 3 * R * n_global + R * n_global   # x, v, density
 
     if rank == 0:
         peak, peak_src = load_peaks()
