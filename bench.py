@@ -10,7 +10,8 @@ block (SURVEY.md 8d).  One "step" = one TimeStepDFSPH::step() (search + divergen
             inside the timed region).
 `roofline`: dominant kernel class, algorithmic bytes / its CUDA-event launch duration / measured HBM peak.
 `cpu_baseline`: the reference's own DFSPH sources (oracle/_ref, built by oracle/Makefile; neighbour search = our
-            CompactNSearch-compatible stand-in) on the box's host cores, on a bounded sample of the same workload.
+            CompactNSearch-compatible stand-in) on the box's host cores, on a bounded sample of the same workload
+            (1 M-particle block, the same W warm-up steps, then up to 10 timed steps).
 `--impl reference` prints that CPU run as its own JSON line.
 """
 from __future__ import annotations
@@ -197,9 +198,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = run_reference_cpu(args.cpu_sample, args.precision, args.steps, min(args.warmup, 3))
+        # the same W warm-up steps as the B200 arm (the cost of a DFSPH step grows with the phase of the collapse: 2
+        # pressure iterations in the first steps, ~10 after 30 steps at 1 M particles), then up to K timed steps
+        r = run_reference_cpu(args.cpu_sample, args.precision, args.steps, args.warmup, budget_s=40.0)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
-                "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -373,7 +376,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                r = run_reference_cpu(args.cpu_sample, args.precision, 10, 3)
+                r = run_reference_cpu(args.cpu_sample, args.precision, min(args.steps, 10), args.warmup, budget_s=15.0)
                 line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the CPU leg must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
