@@ -36,8 +36,8 @@ typedef enum {
     DFSPH_B200_ERR_COMM = -5          /* multi-GPU exchange failed */
 } dfsph_b200_status;
 
-/* Kernel ids use the reference's enum values (SPlisHSPlasH/Simulation.cpp:215-253). */
-/* Simulation "kernel" / "gradKernel" ids of the 3-D build (Simulation.cpp:221-228, 241-248) */
+/* Kernel ids use the reference's enum values: Simulation "kernel" / "gradKernel" of the 3-D build
+ * (SPlisHSPlasH/Simulation.cpp:221-228, 241-248). */
 enum { DFSPH_B200_KERNEL_CUBIC = 0, DFSPH_B200_KERNEL_WENDLAND_QUINTIC_C2 = 1, DFSPH_B200_KERNEL_POLY6 = 2,
        DFSPH_B200_KERNEL_SPIKY = 3, DFSPH_B200_KERNEL_PRECOMPUTED_CUBIC = 4 };
 
@@ -73,7 +73,7 @@ typedef struct {
     int32_t max_boundary_neighbors; /* per-particle neighbour-table capacity, boundary set (0 = default 64) */
     double domain_min[3];           /* cell-grid extent; if min == max it is derived from the particle sets at */
     double domain_max[3];           /*   the first step (particles that leave it are clamped to the edge cells) */
-    int32_t rank;                   /* multi-GPU slab decomposition along x: this context's slab (0 for single GPU) */
+    int32_t rank;                   /* multi-GPU slab decomposition (axis and bounds: dfsph_b200_comm_init): this context's slab (0 for single GPU) */
     int32_t world_size;             /* number of slabs (1 for single GPU) */
     int32_t grad_kernel;            /* Simulation "gradKernel" (setGradKernel, Simulation.cpp:306-336), same ids;
                                        -1 (dfsph_b200_default_config) = same as `kernel` */
@@ -127,7 +127,9 @@ const char* dfsph_b200_last_error(const dfsph_b200_ctx* ctx);  /* ctx may be NUL
 
 /* Replaces: FluidModel::initModel -> add_point_set(x, n, dynamic, search, find) (FluidModel.cpp:285-327) and
  * SimulationDataDFSPH::init (DFSPH/SimulationDataDFSPH.cpp:22-60).  x, v: AoS Real[3*n] (Eigen DontAlign layout,
- * Common.h:27); v, id, state may be NULL (zero velocity, id = index, Active).  kappa/kappa_v start at 0. */
+ * Common.h:27); v, id, state may be NULL (zero velocity, id = index, Active).  kappa/kappa_v start at 0.
+ * May be called again to restart a run (SimulatorBase::reset -> TimeStep::reset): device capacity, boundary sets and,
+ * in multi-GPU contexts, the communicator and peer mappings are kept (every rank must re-submit its slab). */
 int dfsph_b200_set_fluid(dfsph_b200_ctx* ctx, uint64_t n, const void* x, const void* v,
                          const uint32_t* id, const uint32_t* state, double density0, double volume);
 
