@@ -231,8 +231,8 @@ def main():
         sc = scenes.dam_break(args.particles, dtype=dt)
         ts = build_b200_scene(sc, args.precision, device=local_rank, **solver_params())
     else:
-        # weak scaling: `world` blocks of the named size side by side in one tank, one x-slab per GPU, ghost exchange and
-        # migration over NCCL inside the library (splishsplash_b200/csrc/multi_gpu.cuh)
+        # weak scaling: `world` blocks of the named size side by side in one tank (strong: one block cut into `world`
+        # slabs), one slab per GPU; migration and ghost exchange happen inside the library (csrc/multi_gpu.cuh)
         from splishsplash_b200 import parallel
         if args.scaling == "weak":
             sc = scenes.dam_break_weak(rank, world, args.particles, dtype=dt)
@@ -241,6 +241,8 @@ def main():
         ts = parallel.build_b200_slab(sc, args.precision, rank, world, device=local_rank, **solver_params())
     n = ts.num_particles
     n_global = n if world == 1 else sc["global_particles"]
+    cfg["particles_per_gpu"] = int(n_global // world)
+    cfg["particles_total"] = int(n_global)
 
     def barrier():
         ts.synchronize()
@@ -252,8 +254,9 @@ def main():
         PROGRESS["step"] = k
         ts.step(1)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # one nvidia-smi poller per job, not per rank
+    if sampler:
+        sampler.start()
     ts.set_profiling(True)
     ts.timer_start()
     launches = 0
@@ -268,7 +271,7 @@ def main():
         ms_search += st.ms_search
         ms_solver += st.ms_solver
     ms = ts.timer_stop()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     prof = ts.profile()
     ts.set_profiling(False)
     barrier()
