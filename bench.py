@@ -353,6 +353,7 @@ def main():
         nv = float(np.mean([i[0] for i in iters]))
         npr = float(np.mean([i[1] for i in iters]))
         step_bytes = ((101 + 17 * (nv + npr)) * R + 32) * n
+        traffic = NCU_TRAFFIC.get((dom, args.precision, args.particles))
         line = {
             "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -367,7 +368,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((dom, args.precision, args.particles)),
+                         "frac": achieved / peak, "traffic": traffic,
+                         # actual DRAM bytes (ncu capture, mostly the neighbour-index table) over the live launch time
+                         "dram_frac": (traffic / (dms / dcnt * 1e-3) / 1e9 / peak) if (traffic and dcnt) else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": dms / dcnt if dcnt else None, "share_of_step": dms / total_ms if total_ms else None},
             "roofline_step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
