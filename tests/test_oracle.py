@@ -136,3 +136,64 @@ def test_named_blocks_and_boundary():
     assert on_face.all()
     # nearest fluid particle one diameter from the adjacent walls
     assert np.allclose(sc["fluid_x"].min(axis=0), lo + 0.05, atol=1e-6)
+
+
+# ---- the neighbour search of the oracle against an O(N^2) evaluation of the predicate --------------------------
+def _brute_force_sets(x, y, radius, dt, exclude_self):
+    """{i: sorted j} with l2 = dx*dx; l2 += dy*dy; l2 += dz*dz; l2 < R*R evaluated in Real without FMA (numpy does not fuse),
+    R = 4 r in Real (Simulation.cpp:283)."""
+    R = dt(4.0) * dt(radius)
+    r2 = R * R
+    counts = np.zeros(len(x), dtype=np.int64)
+    lists = []
+    for a in range(0, len(x), 512):
+        d = x[a:a + 512, None, :] - y[None, :, :]
+        l2 = d[..., 0] * d[..., 0]
+        l2 = l2 + d[..., 1] * d[..., 1]
+        l2 = l2 + d[..., 2] * d[..., 2]
+        m = l2 < r2
+        if exclude_self:
+            idx = np.arange(a, min(a + 512, len(x)))
+            m[idx - a, idx] = False
+        counts[a:a + 512] = m.sum(axis=1)
+        lists.append(np.nonzero(m))
+    rows = np.concatenate([a * 512 + l[0] for a, l in enumerate(lists)])
+    cols = np.concatenate([l[1] for l in lists])
+    return counts, rows, cols
+
+
+@pytest.mark.parametrize("prec,which", [("f64", "ref"), ("f32", "ref"), ("f64", "port"), ("f32", "port")])
+def test_oracle_neighbour_search_matches_brute_force(prec, which):
+    """Lattice scene (many pairs exactly at the support radius: strict '<'), then the same particles jittered."""
+    avail = refsim.ref_available(prec) if which == "ref" else portsim.port_available(prec)
+    if not avail:
+        pytest.skip("oracle library not present")
+    dt = np.float32 if prec == "f32" else np.float64
+    rng = np.random.default_rng(3)
+    for jitter in (0.0, 0.3):
+        sc = scenes.dam_break("small", dtype=dt)
+        if jitter:
+            sc["fluid_x"] = (sc["fluid_x"] + rng.uniform(-jitter, jitter, sc["fluid_x"].shape) * sc["radius"]).astype(dt)
+        build = refsim.build_ref_scene if which == "ref" else portsim.build_port_scene
+        sim = build(sc, prec, kernel=4)
+        try:
+            sim.search_and_density()
+            ids = sim.ids()
+            x = sim.field_by_id("position")
+            # fluid-fluid
+            c, o, i = sim.neighbors(0, 0)
+            nc, nl = neighbor_sets_by_id(c, o, i, ids, ids)
+            bc, rows, cols = _brute_force_sets(x, x, sc["radius"], dt, True)
+            assert np.array_equal(nc, bc)
+            order = np.lexsort((cols, rows))
+            assert np.array_equal(nl, cols[order].astype(nl.dtype))
+            # fluid-boundary (indices of the oracle's own boundary array)
+            bx, _ = sim.boundary(0)
+            c, o, i = sim.neighbors(0, 1)
+            nc, nl = neighbor_sets_by_id(c, o, i, ids, None)
+            bc, rows, cols = _brute_force_sets(x, bx, sc["radius"], dt, False)
+            assert np.array_equal(nc, bc)
+            order = np.lexsort((cols, rows))
+            assert np.array_equal(nl, cols[order].astype(nl.dtype))
+        finally:
+            sim.destroy()
