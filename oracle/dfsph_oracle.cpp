@@ -775,6 +775,24 @@ double ref_w_zero() { return g->simW_zero; }
 double ref_fluid_volume(int) { return g->V; }
 int ref_kernel() { return g->kernel; }
 
+int ref_eval_kernel(int kind, unsigned n, const Real* r, Real* W, Real* gradW)
+{
+    for (unsigned i = 0; i < n; ++i) {
+        const V3 x = { r[3 * i], r[3 * i + 1], r[3 * i + 2] };
+        Real w; V3 gr;
+        switch (kind) {
+            case 0: w = cubicW(std::sqrt(dot(x, x))); gr = cubicGradW(x); break;
+            case 1: w = wendlandW(std::sqrt(dot(x, x))); gr = wendlandGradW(x); break;
+            case 2: w = poly6W(x); gr = poly6GradW(x); break;
+            case 3: w = spikyW(x); gr = spikyGradW(x); break;
+            case 4: w = lutWf(x); gr = lutGradW(x); break;
+            default: return -1;
+        }
+        W[i] = w; gradW[3 * i] = gr.x; gradW[3 * i + 1] = gr.y; gradW[3 * i + 2] = gr.z;
+    }
+    return 0;
+}
+
 int ref_get_field(int, const char* name, Real* out, int dim)
 {
     const std::string s(name);

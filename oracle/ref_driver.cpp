@@ -266,6 +266,28 @@ double ref_w_zero() { return Simulation::getCurrent()->W_zero(); }
 double ref_fluid_volume(int fluid) { return Simulation::getCurrent()->getFluidModel(fluid)->getVolume(0); }
 int ref_kernel() { return Simulation::getCurrent()->getKernel(); }
 
+/* The reference's kernel classes evaluated pointwise (SPHKernels.h): kind = Simulation "kernel" id 0..4.  Lets the
+   restatement's kernel functions be pinned against the reference's directly (tests/test_oracle.py). */
+int ref_eval_kernel(int kind, unsigned int n, const Real* r, Real* W, Real* gradW)
+{
+	for (unsigned int i = 0; i < n; i++)
+	{
+		const Vector3r x(r[3 * i], r[3 * i + 1], r[3 * i + 2]);
+		Real w; Vector3r g;
+		switch (kind)
+		{
+			case 0: w = CubicKernel::W(x); g = CubicKernel::gradW(x); break;
+			case 1: w = WendlandQuinticC2Kernel::W(x); g = WendlandQuinticC2Kernel::gradW(x); break;
+			case 2: w = Poly6Kernel::W(x); g = Poly6Kernel::gradW(x); break;
+			case 3: w = SpikyKernel::W(x); g = SpikyKernel::gradW(x); break;
+			case 4: w = Simulation::PrecomputedCubicKernel::W(x); g = Simulation::PrecomputedCubicKernel::gradW(x); break;
+			default: return -1;
+		}
+		W[i] = w; gradW[3 * i] = g[0]; gradW[3 * i + 1] = g[1]; gradW[3 * i + 2] = g[2];
+	}
+	return 0;
+}
+
 /* Field names are the reference's own FieldDescription names (FluidModel.cpp:60-66, TimeStepDFSPH.cpp:49-53):
    "position", "velocity", "density", "factor", "advected density", "p / rho^2", "p_v / rho^2",
    "pressure acceleration"; plus "acceleration".  dim = 1 or 3.  Output in current (z-sorted) array order. */

@@ -98,6 +98,17 @@ class RefSim:
         if rc != 0:
             raise RuntimeError(self.lib.ref_last_error().decode())
 
+    def eval_kernel(self, r, kind):
+        """W[n], gradW[n,3] of the kernel with Simulation id `kind` (0 cubic .. 4 precomputed cubic) at the points r."""
+        r = np.ascontiguousarray(r, dtype=self.dtype)
+        W = np.empty(len(r), dtype=self.dtype)
+        g = np.empty((len(r), 3), dtype=self.dtype)
+        self.lib.ref_eval_kernel.restype = C.c_int
+        rc = self.lib.ref_eval_kernel(int(kind), C.c_uint(len(r)), C.c_void_p(r.ctypes.data), C.c_void_p(W.ctypes.data), C.c_void_p(g.ctypes.data))
+        if rc != 0:
+            raise ValueError(f"unknown kernel id {kind}")
+        return W, g
+
     def configure_by_method_id(self, method=7, kernel=4, grad_kernel=None, libdir=None):
         """Select the solver through the reference's own "simulationMethod" enum (needs the library built with
         patches/register_dfsph_b200.patch: oracle/_ref/libsplish_ref_patched_f64.so)."""

@@ -197,3 +197,53 @@ def test_oracle_neighbour_search_matches_brute_force(prec, which):
             assert np.array_equal(nl, cols[order].astype(nl.dtype))
         finally:
             sim.destroy()
+
+
+# ---- kernel functions: the reference's own known-answer tests, and the restatement against the reference pointwise ----------
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_reference_kernel_tests_pass_with_the_oracle_build_flags(prec):
+    """Tests/Kernel/KernelTests.cpp of the reference (normalisation, positivity, AVX vs scalar), compiled unmodified by
+    oracle/Makefile with the flag set of oracle/_ref: the one known-answer test the reference holds for this path."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", f"kerneltests_{prec}")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/kerneltests not built (needs /root/reference)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "All tests passed" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_port_kernels_match_reference_kernels_pointwise(prec):
+    if not (refsim.ref_available(prec) and portsim.port_available(prec)):
+        pytest.skip("oracle/_ref not present")
+    dt = np.float32 if prec == "f32" else np.float64
+    sc = scenes.dam_break("tiny", dtype=dt)
+    ref = refsim.build_ref_scene(sc, prec, kernel=4)
+    port = portsim.build_port_scene(sc, prec, kernel=4)
+    try:
+        R = 4 * sc["radius"]
+        rng = np.random.default_rng(11)
+        r = rng.uniform(-R, R, size=(20000, 3))
+        r[:500] *= 1e-6                                   # around the origin (|r| <= 1e-9 branch of the gradients)
+        r[500:1500] *= (R / np.linalg.norm(r[500:1500], axis=1))[:, None] * rng.uniform(0.999, 1.001, 1000)[:, None]   # around |r| = R
+        r[1500:2500] *= (0.5 * R / np.linalg.norm(r[1500:2500], axis=1))[:, None]                                      # q = 0.5
+        r = r.astype(dt)
+        tol = 2e-6 if prec == "f32" else 1e-13
+        for kind in range(5):
+            Wr, gr = ref.eval_kernel(r, kind)
+            Wp, gp = port.eval_kernel(r, kind)
+            # finite everywhere except where the reference itself divides by |r| = 0 (none of these points)
+            assert np.isfinite(Wr).all() and np.isfinite(gr).all(), kind
+            eW = np.abs(Wp - Wr) / np.abs(Wr).max()
+            eg = np.abs(gp - gr).max(axis=1) / np.abs(gr).max()
+            if kind == 4 and prec == "f32":
+                # the 10 000-slot table is a step function of |r|: where |r| / step sits within one float ulp of an
+                # integer, the reference (FMA-contracted norm) and the restatement (no contraction) may pick adjacent
+                # slots -- a handful of points, each off by at most one table step
+                assert (eW > tol).mean() < 2e-3 and eW.max() < 3e-4, (kind, eW.max())
+                assert (eg > tol).mean() < 2e-3 and eg.max() < 3e-4, (kind, eg.max())
+            else:
+                assert eW.max() <= tol and eg.max() <= tol, (kind, eW.max(), eg.max())
+    finally:
+        ref.destroy()
+        port.destroy()
