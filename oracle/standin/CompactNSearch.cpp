@@ -100,12 +100,21 @@ void NeighborhoodSearch::find_neighbors(bool)
 	{
 		if (!searches[s] && !found[s]) continue;
 		const PointSet& d = m_point_sets[s];
-		for (std::size_t i = 0; i < d.n_points(); ++i)
+		const long n = (long)d.n_points();
+		if (n > 0) any = true;
+		#pragma omp parallel
 		{
-			int c[3];
-			cell_of(d.point((unsigned int)i), c);
-			for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], c[k]); hi[k] = std::max(hi[k], c[k]); }
-			any = true;
+			int tlo[3] = { std::numeric_limits<int>::max(), std::numeric_limits<int>::max(), std::numeric_limits<int>::max() };
+			int thi[3] = { std::numeric_limits<int>::lowest(), std::numeric_limits<int>::lowest(), std::numeric_limits<int>::lowest() };
+			#pragma omp for schedule(static) nowait
+			for (long i = 0; i < n; ++i)
+			{
+				int c[3];
+				cell_of(d.point((unsigned int)i), c);
+				for (int k = 0; k < 3; ++k) { tlo[k] = std::min(tlo[k], c[k]); thi[k] = std::max(thi[k], c[k]); }
+			}
+			#pragma omp critical
+			for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], tlo[k]); hi[k] = std::max(hi[k], thi[k]); }
 		}
 	}
 	for (unsigned int a = 0; a < nsets; ++a)
@@ -133,17 +142,34 @@ void NeighborhoodSearch::find_neighbors(bool)
 		const std::size_t n = d.n_points();
 		std::vector<unsigned int> cid(n);
 		cell_start[s].assign((std::size_t)ncells + 1, 0u);
-		for (std::size_t i = 0; i < n; ++i)
+		// parallel counting sort; every cell segment ends up in ascending point order (= the order a serial pass produces)
+		unsigned int* cnt = cell_start[s].data() + 1;
+		#pragma omp parallel for schedule(static)
+		for (long i = 0; i < (long)n; ++i)
 		{
 			int c[3];
 			cell_of(d.point((unsigned int)i), c);
 			cid[i] = (unsigned int)(((long long)(c[0] - lo[0]) * ny + (c[1] - lo[1])) * nz + (c[2] - lo[2]));
-			cell_start[s][cid[i] + 1]++;
+			#pragma omp atomic
+			cnt[cid[i]]++;
 		}
 		for (long long c = 0; c < ncells; ++c) cell_start[s][c + 1] += cell_start[s][c];
 		sorted[s].resize(n);
 		std::vector<unsigned int> cursor(cell_start[s].begin(), cell_start[s].end() - 1);
-		for (std::size_t i = 0; i < n; ++i) sorted[s][cursor[cid[i]]++] = (unsigned int)i;
+		#pragma omp parallel for schedule(static)
+		for (long i = 0; i < (long)n; ++i)
+		{
+			unsigned int slot;
+			#pragma omp atomic capture
+			slot = cursor[cid[i]]++;
+			sorted[s][slot] = (unsigned int)i;
+		}
+		#pragma omp parallel for schedule(static, 4096)
+		for (long long c = 0; c < ncells; ++c)
+		{
+			const unsigned int k0 = cell_start[s][c], k1 = cell_start[s][c + 1];
+			if (k1 - k0 > 1) std::sort(sorted[s].begin() + k0, sorted[s].begin() + k1);
+		}
 	}
 
 	const Real r2 = m_r2;

@@ -55,35 +55,69 @@ __device__ __forceinline__ void st_real4(Real4* p, Real4 v)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Cell grid: cell edge S >= support radius R (S = R * (1 + 1e-5): two particles that pass the predicate
-// l2 < R*R are then at most one cell apart on every axis even with rounding in the cell computation, which is
-// done in double).  Cells are ordered along a z-order (Morton) curve, two-level so that the cell table stays
-// proportional to the domain (no power-of-two blow-up): 8x8x8-cell blocks are ranked by the Morton code of their
-// block coordinates (host-built rank table), cells inside a block by their 9-bit Morton code (z most significant).
-// Inside a cell, particles are ordered by the Morton code of their 1/8-cell sub-position (search_kernels.cuh), so
-// consecutive lanes of a warp are spatial neighbours and their neighbour lists walk memory in step.
+// Cell grid and particle order.  Cell edge S >= support radius R (S = R * (1 + 1e-5): two particles that pass the
+// predicate l2 < R*R are then at most one cell apart on every axis even with rounding in the cell computation, which is
+// done in double).
+//
+// Particles are stored in PENCIL ORDER: the domain is cut into blocks of DFSPH_BX x DFSPH_BY x DFSPH_BZ cells, blocks
+// are ranked along a z-order curve over their block coordinates (host-built rank table, so the tables stay proportional
+// to the domain), and inside a block the particles are ordered by fine row -- (z, y) at half-cell resolution -- and then
+// by x.  Consecutive particles (= consecutive lanes of a warp) are therefore neighbours ALONG x in a thin pencil, and
+// their neighbour lists are near-translates of each other: at every step of a sweep the lanes of a warp gather from
+// few distinct 128-byte lines (tools/model/wavefront_model.cpp: 7-9 lines per warp-level gather instead of 12 for a
+// Morton order of the cells, on lattice-like states; equal on fully disordered ones).
+//
+// The cell table has one entry per (block, fine row, cell along x, x-slice): DFSPH_FR^2 * DFSPH_XBINS entries per cell.
+// Inside a block the entries of a fine row are contiguous along x, so the neighbour search walks, for each of the
+// (2 FR + 1)^2 fine rows around a particle, ONE run of candidates (two when the run crosses a block face), clipped to
+// the x-slices that can hold a neighbour (search_kernels.cuh).
 // ---------------------------------------------------------------------------------------------------------------
+// all powers of two (the table arithmetic uses shifts)
+#ifndef DFSPH_BX_LOG2
+#define DFSPH_BX_LOG2 4
+#endif
+#ifndef DFSPH_BY_LOG2
+#define DFSPH_BY_LOG2 2
+#endif
+#ifndef DFSPH_BZ_LOG2
+#define DFSPH_BZ_LOG2 2
+#endif
+#define DFSPH_FR_LOG2 1     /* fine rows per cell in y and in z: 2 */
+#ifndef DFSPH_XBINS_LOG2
+#define DFSPH_XBINS_LOG2 1  /* x-slices per cell: 2 */
+#endif
+#define DFSPH_BX (1 << DFSPH_BX_LOG2)
+#define DFSPH_BY (1 << DFSPH_BY_LOG2)
+#define DFSPH_BZ (1 << DFSPH_BZ_LOG2)
+#define DFSPH_FR (1 << DFSPH_FR_LOG2)
+#define DFSPH_XBINS (1 << DFSPH_XBINS_LOG2)
+#define DFSPH_ENTRIES_PER_BLOCK (1u << (DFSPH_BZ_LOG2 + DFSPH_FR_LOG2 + DFSPH_BY_LOG2 + DFSPH_FR_LOG2 + DFSPH_BX_LOG2 + DFSPH_XBINS_LOG2))
+
 struct GridDesc {
     double ox, oy, oz;      // origin
     double inv_cell;        // 1 / S
     int nx, ny, nz;         // cells per axis
     int nby, nbz;           // blocks per axis (y, z)
-    unsigned num_keys;      // nbx * nby * nbz * 512
-    const unsigned* block_rank;   // [nbx*nby*nbz] position of each 8^3-cell block along the z-order curve over blocks
+    unsigned num_keys;      // table entries: blocks * DFSPH_ENTRIES_PER_BLOCK (the dump cell of the slab sort sits behind them)
+    const unsigned* block_rank;   // [nbx*nby*nbz] position of each block along the z-order curve over blocks
 };
 
 __host__ __device__ __forceinline__ unsigned spread3(unsigned v)   // 3 bits -> bits 0,3,6
 {
     return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4);
 }
-__host__ __device__ __forceinline__ unsigned cell_key(int cx, int cy, int cz, const GridDesc& g)
+// table entry of cell (cx, cy, cz), fine row (fy, fz in 0..FR-1) and x-slice xs.  Entries with the same (cy, cz, fy, fz)
+// and cx inside one block are contiguous: entry(cx + 1, .., xs = 0) = entry(cx, .., xs = 0) + DFSPH_XBINS.
+__host__ __device__ __forceinline__ unsigned cell_entry(int cx, int cy, int cz, unsigned fy, unsigned fz, unsigned xs, const GridDesc& g)
 {
-    const unsigned b = ((unsigned)(cx >> 3) * (unsigned)g.nby + (unsigned)(cy >> 3)) * (unsigned)g.nbz + (unsigned)(cz >> 3);
-    const unsigned l = spread3((unsigned)cx & 7u) | (spread3((unsigned)cy & 7u) << 1) | (spread3((unsigned)cz & 7u) << 2);
+    const unsigned ux = (unsigned)cx, uy = (unsigned)cy, uz = (unsigned)cz;
+    const unsigned b = ((ux >> DFSPH_BX_LOG2) * (unsigned)g.nby + (uy >> DFSPH_BY_LOG2)) * (unsigned)g.nbz + (uz >> DFSPH_BZ_LOG2);
+    const unsigned rz = ((uz & (DFSPH_BZ - 1u)) << DFSPH_FR_LOG2) | fz, ry = ((uy & (DFSPH_BY - 1u)) << DFSPH_FR_LOG2) | fy;
+    const unsigned l = ((((rz << (DFSPH_BY_LOG2 + DFSPH_FR_LOG2)) | ry) << DFSPH_BX_LOG2 | (ux & (DFSPH_BX - 1u))) << DFSPH_XBINS_LOG2) | xs;
 #ifdef __CUDA_ARCH__
-    return __ldg(g.block_rank + b) * 512u + l;
+    return __ldg(g.block_rank + b) * DFSPH_ENTRIES_PER_BLOCK + l;
 #else
-    return b * 512u + l;   // host code never needs the curve position
+    return b * DFSPH_ENTRIES_PER_BLOCK + l;   // host code never needs the curve position
 #endif
 }
 __host__ __device__ __forceinline__ int cell_coord(Real x, double o, double inv, int n)
@@ -104,6 +138,17 @@ __host__ __device__ __forceinline__ int cell_coord_fine(Real x, double o, double
     if (c >= n) { c = n - 1; s = 7; }
     sub = (unsigned)(s < 0 ? 0 : (s > 7 ? 7 : s));
     return c;
+}
+// table entry of a position; `xord` receives a key that orders the particles of one entry by x (ties: source index)
+__device__ __forceinline__ unsigned position_entry(const Real4& p, const GridDesc& g, unsigned& xord)
+{
+    unsigned sx, sy, sz;
+    const int cx = cell_coord_fine(p.x, g.ox, g.inv_cell, g.nx, sx);
+    const int cy = cell_coord_fine(p.y, g.oy, g.inv_cell, g.ny, sy);
+    const int cz = cell_coord_fine(p.z, g.oz, g.inv_cell, g.nz, sz);
+    const unsigned fb = __float_as_uint((float)p.x);                 // float order -> unsigned order
+    xord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+    return cell_entry(cx, cy, cz, sy >> (3 - DFSPH_FR_LOG2), sz >> (3 - DFSPH_FR_LOG2), sx >> (3 - DFSPH_XBINS_LOG2), g);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -129,6 +174,7 @@ struct SphConst {
     // 196-204, 268-277)
     int w_kind, g_kind;
     Real gen_k[4], gen_l[4];
+    Real g_a, g_b, g_ml;   // cubic gradient in the form the float sweeps evaluate: 3 l / R^2, -2 l / R^2, -l
 };
 
 // Solver control block, resident in device memory so that no host round trip is needed inside a step.

@@ -47,7 +47,7 @@ struct dfsph_b200_ctx {
     unsigned *cell_count = nullptr, *cell_start = nullptr, *scan_partial = nullptr;
     unsigned keys_cap = 0, scratch_cap = 0;
     bool tables_valid = false;   // neighbour table matches pos[cur_pos]
-    cudaTextureObject_t acc_tex = 0;
+    cudaTextureObject_t acc_tex = 0, pos_tex[2] = {0, 0}, vel_tex[2] = {0, 0};
 
     // boundary (static Akinci2012 particles, all bodies concatenated)
     std::vector<Real4> h_bpos;
@@ -56,6 +56,7 @@ struct dfsph_b200_ctx {
     Real4* bpos = nullptr;
     unsigned* borig = nullptr;
     unsigned* bcell_start = nullptr;
+    unsigned char* bnear = nullptr;   // per cell: a boundary particle in the 3x3x3 neighbourhood
     bool boundary_dirty = true;
 
     double bb_min[3], bb_max[3];
@@ -158,6 +159,7 @@ static void prof_collect(dfsph_b200_ctx* c)   // call after a stream synchronise
 #define CHECK_CTX(ctx) do { if (!(ctx)) return DFSPH_B200_ERR_INVALID; if ((ctx)->sticky) return DFSPH_B200_ERR_CUDA; } while (0)
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+static void destroy_textures(dfsph_b200_ctx* c);
 
 template <typename T>
 static int dev_alloc(dfsph_b200_ctx* c, T** p, size_t count)
@@ -219,6 +221,9 @@ static int setup_constants(dfsph_b200_ctx* c)
     s.l = 48.0f / static_cast<float>(pi * h3);
 #endif
     s.invR2 = s.invR * s.invR;
+    s.g_a = s.l * s.invR2 * static_cast<Real>(3.0);
+    s.g_b = -(s.l * s.invR2 * static_cast<Real>(2.0));
+    s.g_ml = -s.l;
     s.W_zero = host_cubic_W(0, radius, s.k);
     s.V = static_cast<Real>(c->volume);
     s.density0 = static_cast<Real>(c->density0);
@@ -384,11 +389,11 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     for (int k = 0; k < 2; ++k) {
         cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->kappa[k]); cudaFree(c->kappa_v[k]); cudaFree(c->id[k]); cudaFree(c->state[k]);
     }
-    if (c->acc_tex) cudaDestroyTextureObject(c->acc_tex);
+    destroy_textures(c);
     cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
     cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b); cudaFree(c->tcnt_f); cudaFree(c->tcnt_b);
     cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
-    cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start);
+    cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start); cudaFree(c->bnear);
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
     cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->send_l); cudaFree(c->send_r);
     cudaFree(c->send_l2); cudaFree(c->send_r2); cudaFree(c->aux_sl); cudaFree(c->aux_sr); cudaFree(c->aux_rl); cudaFree(c->aux_rr);
@@ -486,10 +491,10 @@ static int setup_grid(dfsph_b200_ctx* c)
         nc[k] = std::max(1, (int)cells);
     }
     g.nx = nc[0]; g.ny = nc[1]; g.nz = nc[2];
-    const unsigned nbx = div_up(g.nx, 8), nby = div_up(g.ny, 8), nbz = div_up(g.nz, 8);
+    const unsigned nbx = div_up(g.nx, DFSPH_BX), nby = div_up(g.ny, DFSPH_BY), nbz = div_up(g.nz, DFSPH_BZ);
     g.nby = (int)nby; g.nbz = (int)nbz;
-    const unsigned long long keys = (unsigned long long)nbx * nby * nbz * 512ull;
-    if (keys > 1500000000ull) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "cell table too large (%llu cells)", keys);
+    const unsigned long long keys = (unsigned long long)nbx * nby * nbz * DFSPH_ENTRIES_PER_BLOCK;
+    if (keys > 3000000000ull) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "cell table too large (%llu entries)", keys);
     g.num_keys = (unsigned)keys;
     {
         // z-order over the blocks: rank of every block's Morton code (z most significant, like the in-block code)
@@ -515,13 +520,14 @@ static int setup_grid(dfsph_b200_ctx* c)
         g.block_rank = c->block_rank;
     }
     c->grid = g;
-    if (g.num_keys + 1 > c->keys_cap) {
-        if (dev_alloc(c, &c->cell_count, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
-        if (dev_alloc(c, &c->cell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
-        if (dev_alloc(c, &c->bcell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
-        if (c->multi && dev_alloc(c, &c->gcell_start, g.num_keys + 8)) return DFSPH_B200_ERR_CUDA;
-        if (dev_alloc(c, &c->scan_partial, div_up(g.num_keys + 1, SCAN_CHUNK) + 8)) return DFSPH_B200_ERR_CUDA;
-        c->keys_cap = g.num_keys + 1;
+    const unsigned nfine = g.num_keys;   // table entries (+ the dump cell)
+    if (nfine + 1 > c->keys_cap) {
+        if (dev_alloc(c, &c->cell_count, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->cell_start, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->bcell_start, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
+        if (c->multi && dev_alloc(c, &c->gcell_start, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->scan_partial, div_up(nfine + 1, SCAN_CHUNK) + 8)) return DFSPH_B200_ERR_CUDA;
+        c->keys_cap = nfine + 1;
     }
     c->grid_valid = true;
     c->boundary_dirty = true;
@@ -586,7 +592,13 @@ static int finalize_boundary(dfsph_b200_ctx* c)
         k_iota<<<div_up(nb, 256), 256, 0, c->stream>>>(tmp_orig, nb);
     }
     int rc = cell_sort(c, tmp, nb, c->bcell_start);
+    if (rc == 0) {
+        const size_t ncell = (size_t)c->grid.nx * c->grid.ny * c->grid.nz;
+        if (dev_alloc(c, &c->bnear, ncell)) rc = DFSPH_B200_ERR_CUDA;
+        else if (cudaMemsetAsync(c->bnear, 0, ncell, c->stream) != cudaSuccess) rc = DFSPH_B200_ERR_CUDA;
+    }
     if (rc == 0 && nb > 0) {
+        k_mark_boundary_cells<<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->grid, tmp, c->bnear);
         k_reorder_boundary<<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->sorted_idx, tmp, tmp_orig, c->bpos, c->borig);
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { c->sticky = 1; c->err = cudaGetErrorString(e); rc = DFSPH_B200_ERR_CUDA; }
@@ -597,6 +609,30 @@ static int finalize_boundary(dfsph_b200_ctx* c)
     c->boundary_dirty = false;
     c->tables_valid = false;
     return 0;
+}
+
+static cudaTextureObject_t make_linear_texture(void* ptr, size_t texels)
+{
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = ptr;
+#if DFSPH_REAL_IS_DOUBLE
+    rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+#else
+    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+#endif
+    rd.res.linear.sizeInBytes = texels * 16;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td)); td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t t = 0;
+    if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) { t = 0; cudaGetLastError(); }
+    return t;
+}
+static void destroy_textures(dfsph_b200_ctx* c)
+{
+    if (c->acc_tex) { cudaDestroyTextureObject(c->acc_tex); c->acc_tex = 0; }
+    for (int k = 0; k < 2; ++k) {
+        if (c->pos_tex[k]) { cudaDestroyTextureObject(c->pos_tex[k]); c->pos_tex[k] = 0; }
+        if (c->vel_tex[k]) { cudaDestroyTextureObject(c->vel_tex[k]); c->vel_tex[k] = 0; }
+    }
 }
 
 static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
@@ -632,20 +668,13 @@ static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
     }
     if (dev_alloc(c, &c->acc, cap + c->ghost_cap + 1)) return DFSPH_B200_ERR_CUDA;
     {
-        // pass B reads a_j through the texture path (16 B texels: one per particle in the float build, two in the double build)
-        if (c->acc_tex) { cudaDestroyTextureObject(c->acc_tex); c->acc_tex = 0; }
+        // the sweeps gather neighbour records through the texture unit (16 B texels: one per particle in the float build,
+        // two in the double build); without a texture the kernels fall back to plain loads
+        destroy_textures(c);
         const size_t texels = ((size_t)cap + c->ghost_cap + 1) * (sizeof(Real4) / 16);
         if (texels < (1ull << 27) && !getenv("DFSPH_B200_NO_TEX")) {   // linear textures address at most 2^27 texels
-            cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
-            rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = c->acc;
-#if DFSPH_REAL_IS_DOUBLE
-            rd.res.linear.desc = cudaCreateChannelDesc<int4>();
-#else
-            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-#endif
-            rd.res.linear.sizeInBytes = texels * 16;
-            cudaTextureDesc td; memset(&td, 0, sizeof(td)); td.readMode = cudaReadModeElementType;
-            if (cudaCreateTextureObject(&c->acc_tex, &rd, &td, nullptr) != cudaSuccess) { c->acc_tex = 0; cudaGetLastError(); }
+            c->acc_tex = make_linear_texture(c->acc, texels);
+            for (int k = 0; k < 2; ++k) { c->pos_tex[k] = make_linear_texture(c->pos[k], texels); c->vel_tex[k] = make_linear_texture(c->vel[k], texels); }
         }
     }
     if (dev_alloc(c, &c->bgrad, cap)) return DFSPH_B200_ERR_CUDA;
@@ -872,7 +901,7 @@ static FluidArrays fluid_arrays(dfsph_b200_ctx* c)
     f.state = c->state[c->cur]; f.nnbr = c->nnbr;
     f.tab_f = c->tab_f; f.cnt_f = c->cnt_f; f.tab_b = c->tab_b; f.cnt_b = c->cnt_b; f.tcnt_f = c->tcnt_f; f.tcnt_b = c->tcnt_b;
     f.Kf = c->Kf; f.Kb = c->Kb; f.n = c->n;
-    f.acc_tex = c->acc_tex;
+    f.acc_tex = c->acc_tex; f.pos_tex = c->pos_tex[c->cur_pos]; f.vel_tex = c->vel_tex[c->cur];
     return f;
 }
 
@@ -1091,8 +1120,9 @@ static int run_search(dfsph_b200_ctx* c)
     if (n > 0) {
         ProfScope ps(c, DFSPH_B200_PROF_BUILD);
         k_build_neighbors<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
-            c->bpos, c->bcell_start, c->nb, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
-            c->ng, c->gcell_start, c->sorted_idx);
+            c->bpos, c->bcell_start, c->nb, c->bnear, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
+            c->ng, c->gcell_start, c->sorted_idx, c->slab_axis,
+            c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300);
         c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());

@@ -92,15 +92,12 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash_slab(const Real4* __r
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Real4 p = pos[i];
-    unsigned sx, sy, sz;
-    const int cx = cell_coord_fine(p.x, g.ox, g.inv_cell, g.nx, sx);
-    const int cy = cell_coord_fine(p.y, g.oy, g.inv_cell, g.ny, sy);
-    const int cz = cell_coord_fine(p.z, g.oz, g.inv_cell, g.nz, sz);
-    unsigned key = cell_key(cx, cy, cz, g);
+    unsigned xord;
+    unsigned key = position_entry(p, g, xord);
     const double x = slab_coord(p, axis);
     if ((has_left && x < lo) || (has_right && x >= hi)) key = g.num_keys;
     key_out[i] = key;
-    fine_out[i] = spread3(sx) | (spread3(sy) << 1) | (spread3(sz) << 2);
+    fine_out[i] = xord;
     rank_out[i] = atomicAdd(cell_count + key, 1u);
 }
 

@@ -1,9 +1,9 @@
 // Neighbourhood search on the device (replaces CompactNSearch::find_neighbors / z_sort /
 // sort_field called from SPlisHSPlasH/Simulation.cpp:606-642 and SPlisHSPlasH/FluidModel.cpp:329-360):
-//   cell key (blocked z-order) -> counting sort (histogram, exclusive scan = cell-start table, scatter, per-cell
-//   fix-up that makes the permutation deterministic) -> reorder of the persistent particle arrays -> per-particle
-//   neighbour table for the solver sweeps, laid out warp-tile interleaved so that every table read is a coalesced
-//   128 B line.  Predicate (CompactNSearch contract, see oracle/standin/CompactNSearch.h):
+//   table entry (pencil order, common.cuh) -> counting sort (histogram, exclusive scan = cell-start table, scatter,
+//   per-entry fix-up that orders every entry by x and makes the permutation deterministic) -> reorder of the persistent
+//   particle arrays -> per-particle neighbour table for the solver sweeps, laid out warp-tile interleaved so that every
+//   table read is a coalesced 128 B line.  Predicate (CompactNSearch contract, see oracle/standin/CompactNSearch.h):
 //   l2 = dx*dx; l2 += dy*dy; l2 += dz*dz  with every operation rounded in Real (no FMA), neighbour iff l2 < R*R.
 #pragma once
 #include "common.cuh"
@@ -110,13 +110,10 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash(const Real4* __restri
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Real4 p = pos[i];
-    unsigned sx, sy, sz;
-    const int cx = cell_coord_fine(p.x, g.ox, g.inv_cell, g.nx, sx);
-    const int cy = cell_coord_fine(p.y, g.oy, g.inv_cell, g.ny, sy);
-    const int cz = cell_coord_fine(p.z, g.oz, g.inv_cell, g.nz, sz);
-    const unsigned key = cell_key(cx, cy, cz, g);
+    unsigned xord;
+    const unsigned key = position_entry(p, g, xord);
     key_out[i] = key;
-    fine_out[i] = spread3(sx) | (spread3(sy) << 1) | (spread3(sz) << 2);
+    fine_out[i] = xord;
     rank_out[i] = atomicAdd(cell_count + key, 1u);
 }
 
@@ -128,9 +125,9 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_scatter(const unsigned* __
     sorted_idx[cell_start[key[i]] + rank[i]] = i;
 }
 
-// The atomic ranks above depend on thread scheduling.  Sorting every cell segment by (sub-cell Morton code, source
-// index) makes the permutation -- and with it every floating-point summation order downstream -- reproducible run to
-// run, and continues the z-order curve below the cell level.
+// The atomic ranks above depend on thread scheduling.  Sorting every table entry's segment by (x, source index) makes
+// the permutation -- and with it every floating-point summation order downstream -- reproducible run to run, and
+// completes the pencil order (a fine row is sorted by x across its entries).
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_fix_order(const unsigned* __restrict__ cell_start, unsigned num_keys,
                                                                   const unsigned* __restrict__ fine, unsigned* __restrict__ sorted_idx)
 {
@@ -207,52 +204,139 @@ __device__ __forceinline__ bool neighbor_predicate(Real4 a, Real4 b, Real R2)
     return l2 < R2;
 }
 
-// One thread per particle of the searching set; walks the 27 cells around its cell in the `other` set's cell table.
+// Candidate walk.  Calls f(k) for every slot k of the point set behind `cs` (a cell-start table in pencil order) that can
+// hold a neighbour of position xi: for each of the (2 FR + 1)^2 fine rows around the particle, the distance of the
+// particle to the row bounds |dx| of any neighbour in it; rows that cannot hold one are skipped and the others are
+// clipped to the x-slices inside the bound.  Inside a block a fine row is one contiguous run of slots sorted by x (two
+// runs when the clipped range crosses a block face); both runs are walked by ONE flat loop so that lanes with one and
+// with two runs stay in step.  The clipping is conservative (margins far above the rounding of the exact predicate and
+// of the double-precision cell coordinates); the caller's predicate decides membership.  This leaves ~45 % of the
+// candidates of a plain 27-cell walk.
+template <class F>
+__device__ __forceinline__ void walk_candidates(const Real4 xi, const GridDesc& g, const unsigned* __restrict__ cs, F& f)
+{
+    // cell coordinates in double exactly as the cell sort computes them (clamped to the grid)
+    const double tx = ((double)xi.x - g.ox) * g.inv_cell, ty = ((double)xi.y - g.oy) * g.inv_cell, tz = ((double)xi.z - g.oz) * g.inv_cell;
+    const double flx = floor(tx), fly = floor(ty), flz = floor(tz);
+    int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+    float uy = (float)((ty - fly) * (double)DFSPH_FR), uz = (float)((tz - flz) * (double)DFSPH_FR);   // inside the cell, fine-row units
+    float txs = (float)(tx * (double)DFSPH_XBINS);                                                     // x in slice units
+    if (cx < 0) { cx = 0; txs = 0.0f; } if (cx >= g.nx) { cx = g.nx - 1; txs = (float)(g.nx * DFSPH_XBINS) - 0.5f; }
+    if (cy < 0) { cy = 0; uy = 0.0f; } if (cy >= g.ny) { cy = g.ny - 1; uy = (float)DFSPH_FR - 0.001f; }
+    if (cz < 0) { cz = 0; uz = 0.0f; } if (cz >= g.nz) { cz = g.nz - 1; uz = (float)DFSPH_FR - 0.001f; }
+    const int iy = __float2int_rd(uy), iz = __float2int_rd(uz);
+    const int gy = cy * DFSPH_FR + iy, gz = cz * DFSPH_FR + iz;                 // fine row of the particle
+    const float fyf = uy - (float)iy, fzf = uz - (float)iz;                     // position inside the fine row [0, 1)
+    const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx + 1 < g.nx ? cx + 1 : g.nx - 1;
+    const int f0 = x0 * DFSPH_XBINS, f1 = x1 * DFSPH_XBINS + DFSPH_XBINS - 1;
+    const int nry = g.ny * DFSPH_FR, nrz = g.nz * DFSPH_FR;
+    // lengths in units of the cell edge S = R (1 + 1e-5): R < S, so the bound R^2 < 1 is conservative; m covers the roundings
+    // (of the float arithmetic here, of rsqrt.approx, and of the predicate itself)
+    const float m = 2.0e-4f, inv_fr = 1.0f / (float)DFSPH_FR;
+    // z outermost / x innermost = ascending entry order inside a block: lists come out (nearly) sorted by address
+    for (int dz = -DFSPH_FR; dz <= DFSPH_FR; ++dz) {
+        const int rz = gz + dz;
+        if (rz < 0 || rz >= nrz) continue;
+        const float az = dz < 0 ? fzf + (float)(-dz - 1) : (1.0f - fzf) + (float)(dz - 1);
+        const float pz = dz == 0 ? 0.0f : fmaxf(az * inv_fr - m, 0.0f);
+        const float wz2 = 1.0f - pz * pz;
+        if (wz2 <= 0.0f) continue;
+        const unsigned czr = (unsigned)rz >> DFSPH_FR_LOG2, fzr = (unsigned)rz & (DFSPH_FR - 1u);
+#pragma unroll
+        for (int dy = -DFSPH_FR; dy <= DFSPH_FR; ++dy) {
+            const int ry = gy + dy;
+            const float ay = dy < 0 ? fyf + (float)(-dy - 1) : (1.0f - fyf) + (float)(dy - 1);
+            const float py = dy == 0 ? 0.0f : fmaxf(ay * inv_fr - m, 0.0f);
+            const float w2 = wz2 - py * py;
+            if (ry < 0 || ry >= nry || w2 <= 0.0f) continue;                      // outside the grid / the whole row is farther than R
+            const float ws = (w2 * fast_rsqrt(w2) + m) * (float)DFSPH_XBINS + 0.02f;   // |dx| bound in slices (+ float rounding of txs)
+            int fa = __float2int_rd(txs - ws), fb = __float2int_rd(txs + ws);
+            fa = fa < f0 ? f0 : fa; fb = fb > f1 ? f1 : fb;
+            if (fa > fb) continue;
+            const unsigned ca = (unsigned)fa >> DFSPH_XBINS_LOG2, cb = (unsigned)fb >> DFSPH_XBINS_LOG2;
+            const unsigned cyr = (unsigned)ry >> DFSPH_FR_LOG2, fyr = (unsigned)ry & (DFSPH_FR - 1u);
+            // up to two runs: [s1, e1) in ca's block and [s2, e2) in the next block along x
+            const unsigned ka = cell_entry((int)ca, (int)cyr, (int)czr, fyr, fzr, 0u, g);
+            unsigned s1 = __ldg(cs + ka + ((unsigned)fa - (ca << DFSPH_XBINS_LOG2))), e1, s2 = 0u, e2 = 0u;
+            if ((ca >> DFSPH_BX_LOG2) == (cb >> DFSPH_BX_LOG2)) {
+                e1 = __ldg(cs + ka + ((unsigned)fb - (ca << DFSPH_XBINS_LOG2)) + 1u);
+            } else {
+                const unsigned xs = (cb >> DFSPH_BX_LOG2) << DFSPH_BX_LOG2;          // first cell of the next block
+                e1 = __ldg(cs + ka + ((xs - ca) << DFSPH_XBINS_LOG2));                // start of the entry behind the row's last cell in this block
+                const unsigned kb = cell_entry((int)xs, (int)cyr, (int)czr, fyr, fzr, 0u, g);
+                s2 = __ldg(cs + kb);
+                e2 = __ldg(cs + kb + ((unsigned)fb - (xs << DFSPH_XBINS_LOG2)) + 1u);
+            }
+            unsigned rem = (e1 - s1) + (e2 - s2);
+            unsigned k = s1;
+            if (s1 == e1) { k = s2; e1 = 0xffffffffu; }
+            for (; rem > 0u; --rem) {
+                const unsigned kk = k;
+                ++k;
+                if (k == e1) k = s2;
+                f(kk);
+            }
+        }
+    }
+}
+
+// Functor of the table build: exact predicate, predicated (branch-free) store into the warp-tile interleaved table.
 // SELF: searching set == found set (skip j == i).
 // PERM: the found set is not stored in cell order; `perm` maps cell-table slots to its particles (ghost set) and the
 // table receives `base + particle`.  `cnt` continues an existing list (ghosts are appended to the fluid list).
+template <bool SELF, bool PERM>
+struct BuildF {
+    Real4 xi; unsigned i; Real R2;
+    const Real4* __restrict__ other_pos; const unsigned* __restrict__ perm;
+    unsigned* my; unsigned K, base, cnt;
+    __device__ __forceinline__ void operator()(unsigned k)
+    {
+        const unsigned j = PERM ? __ldg(perm + k) : k;
+        const Real4 xj = ld_gather(other_pos + j);
+        const bool hit = neighbor_predicate(xi, xj, R2) && !(SELF && j == i);
+        // a divergent branch per candidate costs more than the store: predicate it
+        unsigned* dst = my + (size_t)cnt * DFSPH_TILE;
+        asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.u32 [%1], %2; }"
+                     :: "r"((unsigned)(hit && cnt < K)), "l"(dst), "r"(base + j) : "memory");
+        cnt += hit ? 1u : 0u;
+    }
+};
+
 template <bool SELF, bool PERM>
 __device__ __forceinline__ unsigned search_cells(const Real4 xi, unsigned i, const GridDesc& g, Real R2,
     const Real4* __restrict__ other_pos, const unsigned* __restrict__ other_cell_start,
     unsigned* __restrict__ tab, unsigned K, unsigned tile, unsigned lane,
     unsigned cnt = 0, const unsigned* __restrict__ perm = nullptr, unsigned base = 0)
 {
-    const int cx = cell_coord(xi.x, g.ox, g.inv_cell, g.nx);
-    const int cy = cell_coord(xi.y, g.oy, g.inv_cell, g.ny);
-    const int cz = cell_coord(xi.z, g.oz, g.inv_cell, g.nz);
-    unsigned* my = tab + (size_t)tile * K * DFSPH_TILE + lane;
-    // z outermost / x innermost = ascending Morton order inside a block: lists come out (nearly) sorted by address
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int z = cz + dz;
-        if (z < 0 || z >= g.nz) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int y = cy + dy;
-            if (y < 0 || y >= g.ny) continue;
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int x = cx + dx;
-                if (x < 0 || x >= g.nx) continue;
-                const unsigned key = cell_key(x, y, z, g);
-                const unsigned s = __ldg(other_cell_start + key), e = __ldg(other_cell_start + key + 1);
-                for (unsigned k = s; k < e; ++k) {
-                    const unsigned j = PERM ? __ldg(perm + k) : k;
-                    const Real4 xj = ld_gather(other_pos + j);
-                    if (neighbor_predicate(xi, xj, R2) && !(SELF && j == i)) {
-                        if (cnt < K) my[(size_t)cnt * DFSPH_TILE] = base + j;
-                        ++cnt;
-                    }
-                }
-            }
-        }
-    }
-    return cnt;
+    BuildF<SELF, PERM> f{xi, i, R2, other_pos, perm, tab + (size_t)tile * K * DFSPH_TILE + lane, K, base, cnt};
+    walk_candidates(xi, g, other_cell_start, f);
+    return f.cnt;
 }
 
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_build_neighbors(unsigned n, GridDesc g, Real R2,
+// Static boundaries: marks every cell that has a boundary particle in its 3x3x3 neighbourhood, so that the table build
+// only walks the boundary set for fluid particles near a wall (one byte per cell, linear index (cx ny + cy) nz + cz).
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_mark_boundary_cells(unsigned nb, GridDesc g, const Real4* __restrict__ bpos, unsigned char* __restrict__ near)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const Real4 p = bpos[i];
+    const int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx), cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny), cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+    for (int x = max(cx - 1, 0); x <= min(cx + 1, g.nx - 1); ++x)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y)
+            for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
+                near[((size_t)x * g.ny + y) * g.nz + z] = 1;
+}
+
+// ghost_lo / ghost_hi: (multi-GPU) only particles within one cell of a slab face can have ghost neighbours
+#ifndef DFSPH_BUILD_MIN_BLOCKS
+#define DFSPH_BUILD_MIN_BLOCKS 5   /* 48 registers: the kernel is latency-bound between the table loads of a row and its candidates (2.29 -> 2.13 ms at 10 M) */
+#endif
+__global__ void __launch_bounds__(DFSPH_BLOCK, DFSPH_BUILD_MIN_BLOCKS) k_build_neighbors(unsigned n, GridDesc g, Real R2,
     const Real4* __restrict__ pos, const unsigned* __restrict__ cell_start,
-    const Real4* __restrict__ bpos, const unsigned* __restrict__ bcell_start, unsigned nb,
+    const Real4* __restrict__ bpos, const unsigned* __restrict__ bcell_start, unsigned nb, const unsigned char* __restrict__ bnear,
     unsigned* __restrict__ tab_f, unsigned Kf, unsigned* __restrict__ tab_b, unsigned Kb,
     unsigned* __restrict__ cnt_f, unsigned* __restrict__ cnt_b, unsigned* __restrict__ tcnt_f, unsigned* __restrict__ tcnt_b, Ctrl* ctrl,
-    unsigned ng, const unsigned* __restrict__ gcell_start, const unsigned* __restrict__ gperm)
+    unsigned ng, const unsigned* __restrict__ gcell_start, const unsigned* __restrict__ gperm, int slab_axis, double ghost_lo, double ghost_hi)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -260,9 +344,15 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_build_neighbors(unsigned n, Gri
     const Real4 xi = ld_gather(pos + i);
     unsigned cf = search_cells<true, false>(xi, i, g, R2, pos, cell_start, tab_f, Kf, tile, lane);
     // multi-GPU: ghost particles of the neighbouring slabs live behind the owned ones at pos[n .. n+ng)
-    if (ng > 0) cf = search_cells<false, true>(xi, i, g, R2, pos + n, gcell_start, tab_f, Kf, tile, lane, cf, gperm, n);
+    if (ng > 0) {
+        const double a = slab_axis == 0 ? (double)xi.x : (slab_axis == 1 ? (double)xi.y : (double)xi.z);
+        if (a < ghost_lo || a > ghost_hi) cf = search_cells<false, true>(xi, i, g, R2, pos + n, gcell_start, tab_f, Kf, tile, lane, cf, gperm, n);
+    }
     unsigned cb = 0;
-    if (nb > 0) cb = search_cells<false, false>(xi, i, g, R2, bpos, bcell_start, tab_b, Kb, tile, lane);
+    if (nb > 0) {
+        const int cx = cell_coord(xi.x, g.ox, g.inv_cell, g.nx), cy = cell_coord(xi.y, g.oy, g.inv_cell, g.ny), cz = cell_coord(xi.z, g.oz, g.inv_cell, g.nz);
+        if (bnear[((size_t)cx * g.ny + cy) * g.nz + cz]) cb = search_cells<false, false>(xi, i, g, R2, bpos, bcell_start, tab_b, Kb, tile, lane);
+    }
     const unsigned sf = cf < Kf ? cf : Kf, sb = cb < Kb ? cb : Kb;
     cnt_f[i] = sf;
     cnt_b[i] = sb;

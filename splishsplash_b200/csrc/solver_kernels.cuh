@@ -60,8 +60,44 @@ struct FluidArrays {
     const unsigned* tcnt_b;
     unsigned Kf, Kb;
     unsigned n;
-    cudaTextureObject_t acc_tex;   // float build: pass B fetches a_j through the texture path (0 = plain loads)
+    cudaTextureObject_t acc_tex;   // linear textures over acc / pos / vel (0 = none: plain loads).  Scattered gathers through the
+    cudaTextureObject_t pos_tex;   // texture unit cost fewer L1 data-pipe wavefronts than LDG.128 (profiles/r2_tex_microbench.md)
+    cudaTextureObject_t vel_tex;
 };
+
+// Which L1 front end each scattered gather uses (1 = texture unit, 0 = LSU).  Compile-time so that tuning builds can be
+// compared (tools/variant_bench.py).
+#ifndef DFSPH_TEX_POS_A
+#define DFSPH_TEX_POS_A 0   /* (x_j, kappa_j) in pressure_accel: pass A and the two finalisers */
+#endif
+#ifndef DFSPH_TEX_POS_B
+#define DFSPH_TEX_POS_B 0   /* x_j in pass B */
+#endif
+#ifndef DFSPH_TEX_ACC_B
+#define DFSPH_TEX_ACC_B 1   /* a_j in pass B */
+#endif
+#ifndef DFSPH_TEX_POS_V
+#define DFSPH_TEX_POS_V 0   /* x_j in the two-array (x, v) sweeps: init sweep, pressure init, viscosity */
+#endif
+#ifndef DFSPH_TEX_VEL
+#define DFSPH_TEX_VEL 1     /* v_j in those sweeps */
+#endif
+
+// PLAIN: the array has a benign in-kernel writer (pos.w), so the LSU fallback must not use the non-coherent path
+template <bool USE_TEX, bool PLAIN>
+__device__ __forceinline__ Real4 gather4(const Real4* __restrict__ base, cudaTextureObject_t tex, unsigned j)
+{
+    if (USE_TEX && tex) {
+#if DFSPH_REAL_IS_DOUBLE
+        const int4 t0 = tex1Dfetch<int4>(tex, (int)(2u * j)), t1 = tex1Dfetch<int4>(tex, (int)(2u * j + 1u));   // 32 B record = two texels
+        return make_real4(__hiloint2double(t0.y, t0.x), __hiloint2double(t0.w, t0.z), __hiloint2double(t1.y, t1.x), __hiloint2double(t1.w, t1.z));
+#else
+        const float4 t = tex1Dfetch<float4>(tex, (int)j);
+        return make_real4(t.x, t.y, t.z, t.w);
+#endif
+    }
+    return PLAIN ? ld_plain(base + j) : ld_gather(base + j);
+}
 
 __device__ __forceinline__ const unsigned* tab_ptr(const unsigned* tab, unsigned K, unsigned i)
 {
@@ -80,7 +116,7 @@ __device__ __forceinline__ void neighbor_sweep(const unsigned* __restrict__ t, u
     for (unsigned k = 0; k < count; k += U) {
         typename F::Data d[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) d[u] = f.load(jn[u]);
+        for (int u = 0; u < U; ++u) d[u] = f.load(jn[u], u);
         if (k + U < count) {
 #pragma unroll
             for (int u = 0; u < U; ++u) jn[u] = __ldg(t + (size_t)(k + U + u) * DFSPH_TILE);
@@ -143,11 +179,18 @@ template <int MODE>
 struct InitFluidF {
     struct Data { Real4 x, v; Real rx, ry, rz, g, W; };
     const Real4* pos; const Real4* vel; const SphConst& c;
+    cudaTextureObject_t pos_tex, vel_tex;
     Real4 xi, vi;
     Real dens, gx, gy, gz, sum_grad2, dadv;
     __device__ __forceinline__ InitFluidF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_)
-        : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), dens(0), gx(0), gy(0), gz(0), sum_grad2(0), dadv(0) {}
-    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.v = ld_gather(vel + j); return d; }
+        : pos(f.pos), vel(f.vel), c(c_), pos_tex(f.pos_tex), vel_tex(f.vel_tex), xi(xi_), vi(vi_), dens(0), gx(0), gy(0), gz(0), sum_grad2(0), dadv(0) {}
+    __device__ __forceinline__ Data load(unsigned j, int slot) const
+    {
+        Data d;
+        d.x = gather4<DFSPH_TEX_POS_V != 0, true>(pos, pos_tex, j);
+        d.v = gather4<DFSPH_TEX_VEL != 0, false>(vel, vel_tex, j);
+        return d;
+    }
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
@@ -183,7 +226,7 @@ struct InitBoundaryF {
     Real dens, bx, by, bz, dadv;
     __device__ __forceinline__ InitBoundaryF(const Real4* bpos_, const SphConst& c_, Real4 xi_, Real4 vi_)
         : bpos(bpos_), c(c_), xi(xi_), vi(vi_), dens(0), bx(0), by(0), bz(0), dadv(0) {}
-    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(bpos + j); return d; }
+    __device__ __forceinline__ Data load(unsigned j, int slot) const { Data d; d.x = ld_gather(bpos + j); return d; }
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
@@ -255,10 +298,16 @@ template <int MODE>
 struct AccelF {
     struct Data { Real4 x; Real rx, ry, rz, g; };
     const Real4* pos; const SphConst& c;
+    cudaTextureObject_t pos_tex;
     Real4 xi;
     Real ax, ay, az;
-    __device__ __forceinline__ AccelF(const FluidArrays& f, const SphConst& c_, Real4 xi_) : pos(f.pos), c(c_), xi(xi_), ax(0), ay(0), az(0) {}
-    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(pos + j); return d; }
+    __device__ __forceinline__ AccelF(const FluidArrays& f, const SphConst& c_, Real4 xi_) : pos(f.pos), c(c_), pos_tex(f.pos_tex), xi(xi_), ax(0), ay(0), az(0) {}
+    __device__ __forceinline__ Data load(unsigned j, int slot) const
+    {
+        Data d;
+        d.x = gather4<DFSPH_TEX_POS_A != 0, false>(pos, pos_tex, j);
+        return d;
+    }
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
@@ -329,26 +378,17 @@ template <int MODE>
 struct JacobiF {
     struct Data { Real4 x, a; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* acc; const SphConst& c;
-    cudaTextureObject_t acc_tex;
+    cudaTextureObject_t acc_tex, pos_tex;
     Real4 xi, ai;
     Real sum;
-    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), acc_tex(f.acc_tex), xi(xi_), ai(ai_), sum(0) {}
-    __device__ __forceinline__ Data load(unsigned j) const
+    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), acc_tex(f.acc_tex), pos_tex(f.pos_tex), xi(xi_), ai(ai_), sum(0) {}
+    __device__ __forceinline__ Data load(unsigned j, int slot) const
     {
+        // The two scattered gathers of pass B: the L1 data pipe is the limiter of this kernel, and a gather through the
+        // texture unit costs fewer wavefronts than LDG.128 (tools/micro/tex_bench.cu).
         Data d;
-        d.x = ld_plain(pos + j);
-#if DFSPH_REAL_IS_DOUBLE
-        if (acc_tex) {   // 32 B record = two 16 B texels
-            const int4 t0 = tex1Dfetch<int4>(acc_tex, (int)(2u * j)), t1 = tex1Dfetch<int4>(acc_tex, (int)(2u * j + 1u));
-            d.a = make_real4(__hiloint2double(t0.y, t0.x), __hiloint2double(t0.w, t0.z), __hiloint2double(t1.y, t1.x), __hiloint2double(t1.w, t1.z));
-        } else d.a = ld_gather(acc + j);
-#else
-        // The two scattered gathers of pass B go through different L1 front ends (LSU for x_j, TEX for a_j): the LSU data
-        // pipe is the limiter of this kernel (ncu: 89-92 %), and the microbenchmark (tools/micro/tex_bench.cu) shows the
-        // mixed form is ~11 % cheaper than two LSU gathers.
-        if (acc_tex) { const float4 t = tex1Dfetch<float4>(acc_tex, (int)j); d.a = make_real4(t.x, t.y, t.z, t.w); }
-        else d.a = ld_gather(acc + j);
-#endif
+        d.x = gather4<DFSPH_TEX_POS_B != 0, true>(pos, pos_tex, j);
+        d.a = gather4<DFSPH_TEX_ACC_B != 0, false>(acc, acc_tex, j);
         return d;
     }
     __device__ __forceinline__ void prep(Data& d) const
@@ -548,11 +588,18 @@ template <int MODE>
 struct ViscosityF {
     struct Data { Real4 x, v; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* vel; const SphConst& c;
+    cudaTextureObject_t pos_tex, vel_tex;
     Real4 xi, vi;
     Real ax, ay, az, eps2, dvisc;
     __device__ __forceinline__ ViscosityF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_, Real dvisc_)
-        : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), ax(0), ay(0), az(0), eps2((Real)0.01 * c_.R * c_.R), dvisc(dvisc_) {}
-    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(pos + j); d.v = ld_gather(vel + j); return d; }
+        : pos(f.pos), vel(f.vel), c(c_), pos_tex(f.pos_tex), vel_tex(f.vel_tex), xi(xi_), vi(vi_), ax(0), ay(0), az(0), eps2((Real)0.01 * c_.R * c_.R), dvisc(dvisc_) {}
+    __device__ __forceinline__ Data load(unsigned j, int slot) const
+    {
+        Data d;
+        d.x = gather4<DFSPH_TEX_POS_V != 0, false>(pos, pos_tex, j);
+        d.v = gather4<DFSPH_TEX_VEL != 0, false>(vel, vel_tex, j);
+        return d;
+    }
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
@@ -577,7 +624,7 @@ struct ViscosityBoundaryF {
     Real ax, ay, az, eps2, coef;
     __device__ __forceinline__ ViscosityBoundaryF(const Real4* bpos_, const SphConst& c_, Real4 xi_, Real4 vi_, Real coef_)
         : bpos(bpos_), c(c_), xi(xi_), vi(vi_), ax(0), ay(0), az(0), eps2((Real)0.01 * c_.R * c_.R), coef(coef_) {}
-    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_gather(bpos + j); return d; }
+    __device__ __forceinline__ Data load(unsigned j, int slot) const { Data d; d.x = ld_gather(bpos + j); return d; }
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
@@ -669,10 +716,17 @@ template <int MODE>
 struct VelDivF {
     struct Data { Real4 x, v; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* vel; const SphConst& c;
+    cudaTextureObject_t pos_tex, vel_tex;
     Real4 xi, vi;
     Real delta;
-    __device__ __forceinline__ VelDivF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_) : pos(f.pos), vel(f.vel), c(c_), xi(xi_), vi(vi_), delta(0) {}
-    __device__ __forceinline__ Data load(unsigned j) const { Data d; d.x = ld_plain(pos + j); d.v = ld_gather(vel + j); return d; }
+    __device__ __forceinline__ VelDivF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 vi_) : pos(f.pos), vel(f.vel), c(c_), pos_tex(f.pos_tex), vel_tex(f.vel_tex), xi(xi_), vi(vi_), delta(0) {}
+    __device__ __forceinline__ Data load(unsigned j, int slot) const
+    {
+        Data d;
+        d.x = gather4<DFSPH_TEX_POS_V != 0, true>(pos, pos_tex, j);
+        d.v = gather4<DFSPH_TEX_VEL != 0, false>(vel, vel_tex, j);
+        return d;
+    }
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
@@ -754,41 +808,28 @@ __global__ void k_step_end(Ctrl* ctrl)
 
 // ---- Akinci2012 boundary volume (BoundaryModel_Akinci2012.cpp:48-75) -------------------------------------------------
 template <int W_MODE>
+struct BoundaryVolumeF {
+    Real4 xi; unsigned i; const SphConst& c; const Real4* __restrict__ bpos; Real delta;
+    __device__ __forceinline__ void operator()(unsigned j)
+    {
+        if (j == i) return;
+        const Real4 xj = ld_gather(bpos + j);
+        // neighbour predicate first (only list members contribute in the reference)
+        if (neighbor_predicate(xi, xj, c.R2)) {
+            const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+            delta += sph_W<W_MODE>(c, rx * rx + ry * ry + rz * rz);
+        }
+    }
+};
+
+template <int W_MODE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_boundary_volume(unsigned nb, GridDesc g, SphConst c, Real W_zero,
     const Real4* __restrict__ bpos, const unsigned* __restrict__ bcell_start, Real* __restrict__ vol_out)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb) return;
     const Real4 xi = ld_gather(bpos + i);
-    const int cx = cell_coord(xi.x, g.ox, g.inv_cell, g.nx);
-    const int cy = cell_coord(xi.y, g.oy, g.inv_cell, g.ny);
-    const int cz = cell_coord(xi.z, g.oz, g.inv_cell, g.nz);
-    Real delta = W_zero;
-    for (int dx = -1; dx <= 1; ++dx) {
-        const int x = cx + dx;
-        if (x < 0 || x >= g.nx) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int y = cy + dy;
-            if (y < 0 || y >= g.ny) continue;
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int z = cz + dz;
-                if (z < 0 || z >= g.nz) continue;
-                const unsigned key = cell_key(x, y, z, g);
-                const unsigned s = bcell_start[key], e = bcell_start[key + 1];
-                for (unsigned j = s; j < e; ++j) {
-                    if (j == i) continue;
-                    const Real4 xj = ld_gather(bpos + j);
-                    // neighbour predicate first (only list members contribute in the reference)
-                    const Real rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
-#if DFSPH_REAL_IS_DOUBLE
-                    double l2 = __dmul_rn(rx, rx); l2 = __dadd_rn(l2, __dmul_rn(ry, ry)); l2 = __dadd_rn(l2, __dmul_rn(rz, rz));
-#else
-                    float l2 = __fmul_rn(rx, rx); l2 = __fadd_rn(l2, __fmul_rn(ry, ry)); l2 = __fadd_rn(l2, __fmul_rn(rz, rz));
-#endif
-                    if (l2 < c.R2) delta += sph_W<W_MODE>(c, rx * rx + ry * ry + rz * rz);
-                }
-            }
-        }
-    }
-    vol_out[i] = (Real)1.0 / delta;
+    BoundaryVolumeF<W_MODE> f{xi, i, c, bpos, W_zero};
+    walk_candidates(xi, g, bcell_start, f);
+    vol_out[i] = (Real)1.0 / f.delta;
 }
