@@ -197,7 +197,7 @@ struct Ctrl {
     unsigned multi;         // 1: multi-GPU run, loop control happens in k_solve_control after the all-reduce
     unsigned long long n_global;   // particles of all ranks (divisor of the average density error)
     unsigned red_seq;       // sequence number of the fused peer-memory all-reduce
-    unsigned pad1;
+    unsigned fatal;         // sticky: a neighbour list did not fit (overflow > capacity); every later kernel of the context is a no-op
 };
 
 struct SolverParams {

@@ -71,6 +71,13 @@ struct dfsph_b200_ctx {
 
     Ctrl* ctrl = nullptr;
     Ctrl* h_ctrl = nullptr;      // pinned
+    bool capacity_error = false; // a neighbour list overflowed (Ctrl::fatal seen on the host): sticky until set_fluid
+    // solver loops as CUDA graphs: k_solve_begin -> WHILE(not done) { pass A, pass B (+ loop control), k_loop_cond }.
+    // One executable graph per (solve, buffer parities); rebuilt when anything baked into the kernel arguments changes.
+    struct SolveGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; unsigned n = 0; };
+    SolveGraph sgraph[2][4];   // [solve][cur * 2 + cur_pos]
+    cudaStream_t capture_stream = nullptr;
+    bool use_graph = true;
     double* partial = nullptr;
     unsigned pred_iter = 2, pred_iter_v = 1;
     unsigned launches = 0;
@@ -160,6 +167,15 @@ static void prof_collect(dfsph_b200_ctx* c)   // call after a stream synchronise
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 static void destroy_textures(dfsph_b200_ctx* c);
+static void invalidate_graphs(dfsph_b200_ctx* c)
+{
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 4; ++b) {
+        dfsph_b200_ctx::SolveGraph& g = c->sgraph[a][b];
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+        g.exec = nullptr; g.graph = nullptr; g.n = 0;
+    }
+}
 
 template <typename T>
 static int dev_alloc(dfsph_b200_ctx* c, T** p, size_t count)
@@ -362,6 +378,7 @@ int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out)
     dfsph_b200_ctx* c = new dfsph_b200_ctx();
     c->cfg = *cfg;
     dfsph_b200_default_params(&c->par);
+    c->use_graph = getenv("DFSPH_B200_NO_GRAPH") == nullptr;
     c->Kf = cfg->max_fluid_neighbors > 0 ? (unsigned)cfg->max_fluid_neighbors : 64u;
     c->Kb = cfg->max_boundary_neighbors > 0 ? (unsigned)cfg->max_boundary_neighbors : 64u;
     c->Kf = (c->Kf + DFSPH_PAD - 1u) & ~(DFSPH_PAD - 1u);
@@ -390,6 +407,8 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
         cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->kappa[k]); cudaFree(c->kappa_v[k]); cudaFree(c->id[k]); cudaFree(c->state[k]);
     }
     destroy_textures(c);
+    invalidate_graphs(c);
+    if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
     cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b); cudaFree(c->tcnt_f); cudaFree(c->tcnt_b);
     cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
@@ -637,6 +656,7 @@ static void destroy_textures(dfsph_b200_ctx* c)
 
 static int alloc_fluid(dfsph_b200_ctx* c, unsigned cap)
 {
+    invalidate_graphs(c);   // device pointers are baked into the graphs' kernel arguments
     if (c->multi) {
         // room for one support radius of ghosts per face plus migrants; generous: an eighth of the slab, >= 256 Ki
         c->ghost_cap = std::max(cap / 8u, 262144u);
@@ -751,6 +771,8 @@ int dfsph_b200_set_fluid(dfsph_b200_ctx* c, uint64_t n64, const void* x_, const 
     c->n = n;
     c->density0 = density0;
     c->volume = volume;
+    c->capacity_error = false;
+    invalidate_graphs(c);
     { int rc = setup_constants(c); if (rc) return rc; }
     const Real* x = (const Real*)x_;
     const Real* v = (const Real*)v_;
@@ -870,12 +892,17 @@ int dfsph_b200_set_params(dfsph_b200_ctx* c, const dfsph_b200_params* p)
     if (q.viscosity_method != 0 && q.viscosity_method != 1) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "viscosity_method: only 0 (none) and 1 (Standard viscosity) run on the B200 path");
     if (q.viscosity < 0.0) q.viscosity = 0.0;
     if (q.viscosity_boundary < 0.0) q.viscosity_boundary = 0.0;
-    const bool h_changed = (q.time_step_size != c->par.time_step_size);
     c->par = q;
-    if (h_changed && c->ctrl) {
+    invalidate_graphs(c);   // solver parameters are kernel arguments
+    if (c->ctrl) {
+        // TimeManager::setTimeStepSize always takes effect: compare with the step size the DEVICE holds (the CFL kernel
+        // adapts it), not with the last requested value
         cudaSetDevice(c->cfg.device);
         const Real h = (Real)q.time_step_size;
-        CUDA_TRY(c, cudaMemcpy(&c->ctrl->h, &h, sizeof(Real), cudaMemcpyHostToDevice));
+        Real hd = (Real)0.0;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaMemcpy(&hd, &c->ctrl->h, sizeof(Real), cudaMemcpyDeviceToHost));
+        if (hd != h) CUDA_TRY(c, cudaMemcpy(&c->ctrl->h, &h, sizeof(Real), cudaMemcpyHostToDevice));
     }
     return DFSPH_B200_OK;
 }
@@ -1123,7 +1150,8 @@ static int run_search(dfsph_b200_ctx* c)
             c->bpos, c->bcell_start, c->nb, c->bnear, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
             c->ng, c->gcell_start, c->sorted_idx, c->slab_axis,
             c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300);
-        c->launches++;
+        k_check_capacity<<<1, 1, 0, st>>>(c->ctrl, c->Kf, c->Kb);
+        c->launches += 2;
     }
     CUDA_TRY(c, cudaGetLastError());
     c->tables_valid = true;
@@ -1184,7 +1212,49 @@ static int run_solver(dfsph_b200_ctx* c)
         return 0;
     };
 
+    // Single GPU, not profiling: the loop runs as a CUDA graph -- k_solve_begin, then a WHILE node whose body is pass A,
+    // pass B (which takes the reference's loop decision on the device) and k_loop_cond.  No host synchronisation.
+    auto graph_loop = [&](int solve) -> int {
+        dfsph_b200_ctx::SolveGraph& sg = c->sgraph[solve][c->cur * 2 + c->cur_pos];
+        if (!sg.exec || sg.n != n) {
+            if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+            if (sg.graph) { cudaGraphDestroy(sg.graph); sg.graph = nullptr; }
+            if (!c->capture_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
+            CUDA_TRY(c, cudaGraphCreate(&sg.graph, 0));
+            cudaGraphConditionalHandle handle;
+            CUDA_TRY(c, cudaGraphConditionalHandleCreate(&handle, sg.graph, 1, cudaGraphCondAssignDefault));
+            cudaGraphNode_t n_begin, n_while;
+            {
+                cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
+                void* args[2] = {(void*)&c->ctrl, (void*)&solve};
+                kp.func = (void*)k_solve_begin; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
+                CUDA_TRY(c, cudaGraphAddKernelNode(&n_begin, sg.graph, nullptr, 0, &kp));
+            }
+            cudaGraphNodeParams cp = {};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = handle; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+            CUDA_TRY(c, cudaGraphAddNode(&n_while, sg.graph, &n_begin, 1, &cp));
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            cudaStream_t cs = c->capture_stream;
+            CUDA_TRY(c, cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+            const GhostWait no_wait{nullptr, nullptr, 0u};
+            k_accel<MODE><<<grid, DFSPH_BLOCK, 0, cs>>>(f, c->sph, c->ctrl, nullptr, 0u, nullptr, no_wait);
+            const unsigned gj = std::max(div_up(n, DFSPH_JACOBI_BLOCK), 1u);
+            if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<gj, DFSPH_JACOBI_BLOCK, 0, cs>>>(f, c->sph, sp, c->ctrl, c->partial, nullptr, 0u, nullptr, 0u, 1, no_wait, no_red);
+            else k_jacobi<MODE, SOLVE_PRESS><<<gj, DFSPH_JACOBI_BLOCK, 0, cs>>>(f, c->sph, sp, c->ctrl, c->partial, nullptr, 0u, nullptr, 0u, 1, no_wait, no_red);
+            k_loop_cond<<<1, 1, 0, cs>>>(handle, c->ctrl);
+            cudaGraph_t captured = nullptr;
+            CUDA_TRY(c, cudaStreamEndCapture(cs, &captured));
+            CUDA_TRY(c, cudaGraphInstantiate(&sg.exec, sg.graph, 0));
+            sg.n = n;
+        }
+        CUDA_TRY(c, cudaGraphLaunch(sg.exec, st));
+        c->launches += 1;   // + 3 kernels per iteration, added from the iteration counters when the step's statistics are read
+        return 0;
+    };
+
     auto solve_loop = [&](int solve, unsigned max_it, unsigned& pred) -> int {
+        if (c->use_graph && !multi && !c->profiling) return graph_loop(solve);
         k_solve_begin<<<1, 1, 0, st>>>(c->ctrl, solve);
         c->launches++;
         unsigned launched = 0;
@@ -1307,6 +1377,9 @@ static int run_solver(dfsph_b200_ctx* c)
 
 static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
 {
+    if (c->capacity_error) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "a neighbour list overflowed in an earlier step (need %u fluid / %u boundary slots, have %u / %u): "
+                                    "the state is frozen at that step's start; raise max_*_neighbors and set the fluid again",
+                                    c->h_ctrl->overflow, c->h_ctrl->overflow_b, c->Kf, c->Kb);
     int rc = prepare(c);
     if (rc) return rc;
     if (c->nb > 0 && !c->have_bvol) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "boundary volumes missing: pass V to add_boundary or call compute_boundary_volume");
@@ -1349,11 +1422,15 @@ static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
         stats->num_particles = c->n;
         stats->max_neighbors = hc.max_nbr;
         stats->gpu_launches = c->launches;
+        if (c->use_graph && !c->multi && !c->profiling)   // kernels launched by the loop graphs: pass A, pass B, k_loop_cond per iteration + k_solve_begin
+            stats->gpu_launches += 3u * (hc.iterations + stats->iterations_v) + (c->par.enable_divergence_solver ? 2u : 1u);
         cudaEventElapsedTime(&stats->ms_search, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&stats->ms_solver, c->ev[1], c->ev[2]);
-        if (hc.overflow > c->Kf || hc.overflow_b > c->Kb) {
-            CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "neighbour table capacity exceeded: need %u fluid / %u boundary slots (have %u / %u); raise max_*_neighbors",
-                     hc.overflow, hc.overflow_b, c->Kf, c->Kb);
+        c->par.time_step_size = hc.h;   // what get_params reports: the device's (CFL-adapted) step size
+        if (hc.fatal) {
+            c->capacity_error = true;
+            CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "neighbour table capacity exceeded: need %u fluid / %u boundary slots (have %u / %u); the step was not "
+                     "carried out and the state is frozen; raise max_*_neighbors and set the fluid again", hc.overflow, hc.overflow_b, c->Kf, c->Kb);
         }
     }
     return DFSPH_B200_OK;
@@ -1830,6 +1907,13 @@ int dfsph_b200_synchronize(dfsph_b200_ctx* c)
     CHECK_CTX(c);
     cudaSetDevice(c->cfg.device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->ctrl && !c->capacity_error) {
+        // steps issued without statistics do not synchronise: a neighbour-list overflow is reported here at the latest
+        CUDA_TRY(c, cudaMemcpy(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
+        if (c->h_ctrl->fatal) c->capacity_error = true;
+    }
+    if (c->capacity_error) CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "neighbour table capacity exceeded: need %u fluid / %u boundary slots (have %u / %u); "
+                                    "the state is frozen at the failed step's start", c->h_ctrl->overflow, c->h_ctrl->overflow_b, c->Kf, c->Kb);
     return DFSPH_B200_OK;
 }
 

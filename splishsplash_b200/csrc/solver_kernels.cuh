@@ -247,7 +247,7 @@ template <int MODE, bool DIV_SOLVER>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphConst c, const Real4* __restrict__ bpos, Ctrl* ctrl)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= f.n) return;
+    if (i >= f.n || ctrl->fatal) return;
     const Real4 xi = ld_plain(f.pos + i);   // plain loads: this kernel writes pos.w
     const Real4 vi = ld_gather(f.vel + i);
     const Real V = c.V;
@@ -526,7 +526,7 @@ __global__ void k_solve_control(Ctrl* ctrl, SolverParams sp, SphConst c)
 __global__ void k_solve_begin(Ctrl* ctrl, int solve)
 {
     ctrl->iter = 0;
-    ctrl->done = 0;
+    ctrl->done = ctrl->fatal ? 1 : 0;   // a failed step runs no iteration
     ctrl->ticket = 0;
     if (solve == SOLVE_PRESS) { ctrl->iterations = 0; ctrl->avg_err = 0.0; }
     else { ctrl->iterations_v = 0; ctrl->avg_err_v = 0.0; }
@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_div_final(FluidArrays f, SphCon
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const Real h = ctrl->h;    // still the step's initial h here
     Real velmag = (Real)0.0;
+    if (ctrl->fatal) return;
     if (i < f.n) {
         Real4 v = ld_gather(f.vel + i);
         const unsigned st = f.state[i];
@@ -646,6 +647,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_viscosity_kick(FluidArrays f, S
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const Real h = ctrl->h;
     Real velmag = (Real)0.0;
+    if (ctrl->fatal) { if (i < f.n) st_real4(vel_out + i, ld_gather(f.vel + i)); return; }
     if (i < f.n) {
         const Real4 xi = ld_gather(f.pos + i);
         Real4 v = ld_gather(f.vel + i);
@@ -683,6 +685,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_viscosity_kick(FluidArrays f, S
 __global__ void k_update_time_step(Ctrl* ctrl, SolverParams sp)
 {
     Real h = ctrl->h;
+    if (ctrl->fatal) return;
     ctrl->h_step = h;
     if (sp.cfl_method == 1 || sp.cfl_method == 2) {
 #if DFSPH_REAL_IS_DOUBLE
@@ -748,7 +751,7 @@ template <int MODE>
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_init(FluidArrays f, SphConst c, Ctrl* ctrl)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= f.n) return;
+    if (i >= f.n || ctrl->fatal) return;
     const Real h = ctrl->h;     // the NEW time step size (TimeStepDFSPH.cpp:254)
     const Real4 xi = ld_plain(f.pos + i);
     const Real4 vi = ld_gather(f.vel + i);
@@ -780,6 +783,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_final(FluidArrays f, SphC
     const Real h = ctrl->h;
     const Real hs = ctrl->h_step;
     const Real4 xi = ld_gather(f.pos + i);
+    if (ctrl->fatal) { st_real4(pos_out + i, xi); return; }   // failed step: the state stays where the search left it
     const unsigned st = f.state[i];
     Real ax, ay, az;
     pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
@@ -796,6 +800,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_final(FluidArrays f, SphC
 
 __global__ void k_step_begin(Ctrl* ctrl)
 {
+    if (ctrl->fatal) return;
     ctrl->max_nbr = 0u;
     ctrl->overflow = 0u;
     ctrl->overflow_b = 0u;
@@ -803,7 +808,21 @@ __global__ void k_step_begin(Ctrl* ctrl)
 
 __global__ void k_step_end(Ctrl* ctrl)
 {
+    if (ctrl->fatal) return;
     ctrl->time += (double)ctrl->h_step;      // TimeStepDFSPH.cpp:248
+}
+
+// After the table build: a list that did not fit makes the step -- and the context -- fail instead of running the solver on
+// truncated neighbour sets.  The flag is sticky on the device, so no host round trip is needed to stop the step.
+__global__ void k_check_capacity(Ctrl* ctrl, unsigned Kf, unsigned Kb)
+{
+    if (ctrl->overflow > Kf || ctrl->overflow_b > Kb) ctrl->fatal = 1u;
+}
+
+// Last node of the body of the solver loops' WHILE node (CUDA graph): keep iterating while the loop control says so.
+__global__ void k_loop_cond(cudaGraphConditionalHandle handle, const Ctrl* __restrict__ ctrl)
+{
+    cudaGraphSetConditional(handle, ctrl->done ? 0u : 1u);
 }
 
 // ---- Akinci2012 boundary volume (BoundaryModel_Akinci2012.cpp:48-75) -------------------------------------------------
