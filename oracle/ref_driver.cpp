@@ -410,6 +410,93 @@ int ref_neighbor_checksum(int fluid, int pid, unsigned long long* checksum)
 	return 0;
 }
 
+/* ---- drop-in features (valid after ref_configure_b200): lazy field mirrors, bulk field accessor, device-resident state,
+   CompactNSearch facade ---- */
+static TimeStepDFSPH_B200* b200_ts()
+{
+	if (!g_b200) return nullptr;
+	return dynamic_cast<TimeStepDFSPH_B200*>(Simulation::getCurrent()->getTimeStep());
+}
+int ref_b200_field_downloads() { TimeStepDFSPH_B200* ts = b200_ts(); return ts ? (int)ts->numFieldDownloads() : -1; }
+int ref_b200_set_host_sync(int on)
+{
+	TimeStepDFSPH_B200* ts = b200_ts();
+	if (!ts) return -1;
+	try { ts->setHostStateSync(on != 0); } catch (const std::exception& e) { g_err = e.what(); return -2; }
+	return 0;
+}
+int ref_b200_download_state()
+{
+	TimeStepDFSPH_B200* ts = b200_ts();
+	if (!ts) return -1;
+	try { ts->downloadState(); } catch (const std::exception& e) { g_err = e.what(); return -2; }
+	return 0;
+}
+int ref_b200_download_field(const char* name, void* dst)
+{
+	TimeStepDFSPH_B200* ts = b200_ts();
+	if (!ts) return -1;
+	try { ts->downloadField(name, static_cast<Real*>(dst)); } catch (const std::exception& e) { g_err = e.what(); return -2; }
+	return 0;
+}
+/* Exercises the rest of the CompactNSearch surface of NeighborhoodSearch_B200 the way the reference uses it
+   (add_point_set in model order, set_active, find_neighbors, z_sort + sort_field).  Returns 0 when every check holds,
+   a positive code naming the first failed check otherwise. */
+int ref_b200_facade_selftest()
+{
+	TimeStepDFSPH_B200* ts = b200_ts();
+	if (!ts) return -1;
+	Simulation* sim = Simulation::getCurrent();
+	FluidModel* fm = sim->getFluidModel(0);
+	const unsigned int n = fm->numActiveParticles();
+	try {
+		NeighborhoodSearch_B200 ns(*ts);
+		if (ns.add_point_set(&fm->getPosition(0)[0], n, true, true, true, fm) != 0) return 1;          // FluidModel.cpp:323
+		for (unsigned int b = 0; b < sim->numberOfBoundaryModels(); b++)
+		{
+			BoundaryModel_Akinci2012* bm = static_cast<BoundaryModel_Akinci2012*>(sim->getBoundaryModel(b));
+			if (ns.add_point_set(&bm->getPosition(0)[0], bm->numberOfParticles(), false, false, true, bm) != b + 1) return 2;   // BoundaryModel_Akinci2012.cpp:109
+		}
+		if (ns.n_point_sets() != 1 + sim->numberOfBoundaryModels()) return 3;
+		if (ns.point_set(0).get_user_data() != fm || ns.point_set(0).n_points() != n) return 4;
+		if (!ns.is_active(0, 0) || (ns.n_point_sets() > 1 && (!ns.is_active(0, 1) || ns.is_active(1, 0) || ns.is_active(1, 1)))) return 5;
+		ns.find_neighbors();
+		unsigned long long total0 = 0, total1 = 0;
+		for (unsigned int i = 0; i < n; i++)
+		{
+			const unsigned int c = ns.point_set(0).n_neighbors(0, i);
+			const std::vector<unsigned int>& l = ns.point_set(0).neighbor_list(0, i);
+			if (l.size() != c) return 6;
+			for (unsigned int k = 0; k < c; k++) if (l[k] != ns.point_set(0).neighbor(0, i, k) || (k > 0 && l[k] <= l[k - 1])) return 7;
+			total0 += c;
+			if (ns.n_point_sets() > 1) total1 += ns.point_set(0).n_neighbors(1, i);
+		}
+		if (n > 1 && total0 == 0) return 8;
+		// Simulation.cpp:713-754: switching a pair off empties its lists
+		if (ns.n_point_sets() > 1)
+		{
+			ns.set_active(0u, 1u, false);
+			for (unsigned int i = 0; i < n; i++) if (ns.point_set(0).n_neighbors(1, i) != 0) return 9;
+			ns.set_active(0u, 1u, true);
+			unsigned long long t = 0;
+			for (unsigned int i = 0; i < n; i++) t += ns.point_set(0).n_neighbors(1, i);
+			if (t != total1) return 10;
+		}
+		// z_sort + sort_field (Simulation.cpp:626, FluidModel.cpp:339-346): the permuted id field is the device order
+		ns.z_sort();
+		std::vector<unsigned int> ids(n);
+		for (unsigned int i = 0; i < n; i++) ids[i] = i;
+		ns.point_set(0).sort_field(ids.data());
+		std::vector<char> seen(n, 0);
+		for (unsigned int i = 0; i < n; i++) { if (ids[i] >= n || seen[ids[i]]) return 11; seen[ids[i]] = 1; }
+		std::vector<Real> xs(n);
+		for (unsigned int i = 0; i < n; i++) xs[i] = fm->getPosition(i)[0];
+		ns.point_set(0).sort_field(xs.data());
+		for (unsigned int i = 0; i < n; i++) if (xs[i] != fm->getPosition(ids[i])[0]) return 12;
+	} catch (const std::exception& e) { g_err = e.what(); return -2; }
+	return 0;
+}
+
 int ref_destroy()
 {
 	if (!Simulation::hasCurrent()) return 0;

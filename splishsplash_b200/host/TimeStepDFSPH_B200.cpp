@@ -2,6 +2,8 @@
 #include "dfsph_b200.h"
 #include "SPlisHSPlasH/TimeManager.h"
 #include "SPlisHSPlasH/BoundaryModel_Akinci2012.h"
+#include "SPlisHSPlasH/EmitterSystem.h"
+#include "SPlisHSPlasH/AnimationFieldSystem.h"
 #include "SPlisHSPlasH/Viscosity/Viscosity_Standard.h"
 #include "Utilities/Timing.h"
 #include "Utilities/Counting.h"
@@ -10,6 +12,7 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <algorithm>
+#include <cstring>
 
 using namespace SPH;
 using namespace GenParam;
@@ -37,6 +40,7 @@ struct TimeStepDFSPH_B200::Api
 	decltype(&dfsph_b200_add_boundary) add_boundary;
 	decltype(&dfsph_b200_set_params) set_params;
 	decltype(&dfsph_b200_step_host) step_host;
+	decltype(&dfsph_b200_step) step;
 	decltype(&dfsph_b200_download) download;
 	decltype(&dfsph_b200_upload) upload;
 	decltype(&dfsph_b200_neighbors) neighbors;
@@ -68,6 +72,7 @@ void TimeStepDFSPH_B200::loadLibrary(const std::string& path)
 	resolve(m_lib, m_api->add_boundary, "dfsph_b200_add_boundary");
 	resolve(m_lib, m_api->set_params, "dfsph_b200_set_params");
 	resolve(m_lib, m_api->step_host, "dfsph_b200_step_host");
+	resolve(m_lib, m_api->step, "dfsph_b200_step");
 	resolve(m_lib, m_api->download, "dfsph_b200_download");
 	resolve(m_lib, m_api->upload, "dfsph_b200_upload");
 	resolve(m_lib, m_api->neighbors, "dfsph_b200_neighbors");
@@ -94,7 +99,14 @@ TimeStepDFSPH_B200::TimeStepDFSPH_B200(const std::string& libraryPath) :
 	m_enableDivergenceSolver = true;
 	m_maxIterationsV = 100;
 	m_maxErrorV = static_cast<Real>(0.1);
-	m_syncAllFields = true;
+	m_syncAllFields = false;
+	m_hostStateSync = true;
+	m_hostStateStale = false;
+	m_fieldDownloads = 0;
+	m_uploadedParticles = 0;
+	m_paramsPushed = false;
+	for (int k = 0; k < NUM_MIRRORS; k++) m_stale[k] = false;
+	static_assert(sizeof(dfsph_b200_params) <= sizeof(m_lastParams), "parameter cache too small");
 
 	loadLibrary(libraryPath);
 	resize();
@@ -104,11 +116,11 @@ TimeStepDFSPH_B200::TimeStepDFSPH_B200(const std::string& libraryPath) :
 	if (sim->numberOfFluidModels() > 0)
 	{
 		FluidModel* model = sim->getFluidModel(0);
-		model->addField({ "factor", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_factor[i]; } });
-		model->addField({ "advected density", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_density_adv[i]; } });
-		model->addField({ "p / rho^2", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_pressure_rho2[i]; }, true });
-		model->addField({ "p_v / rho^2", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return &m_pressure_rho2_V[i]; }, true });
-		model->addField({ "pressure acceleration", METHOD_NAME, FieldType::Vector3, [this](const unsigned int i) -> Real* { return &m_pressureAccel[i][0]; } });
+		model->addField({ "factor", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return static_cast<Real*>(mirror(F_FACTOR, i)); } });
+		model->addField({ "advected density", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return static_cast<Real*>(mirror(F_DENSITY_ADV, i)); } });
+		model->addField({ "p / rho^2", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return static_cast<Real*>(mirror(F_KAPPA, i)); }, true });
+		model->addField({ "p_v / rho^2", METHOD_NAME, FieldType::Scalar, [this](const unsigned int i) -> Real* { return static_cast<Real*>(mirror(F_KAPPA_V, i)); }, true });
+		model->addField({ "pressure acceleration", METHOD_NAME, FieldType::Vector3, [this](const unsigned int i) -> Real* { return static_cast<Real*>(mirror(F_PRESSURE_ACCEL, i)); } });
 	}
 }
 
@@ -188,6 +200,7 @@ void TimeStepDFSPH_B200::resize()
 	m_pressure_rho2.assign(n, 0.0);
 	m_pressure_rho2_V.assign(n, 0.0);
 	m_pressureAccel.assign(n, Vector3r::Zero());
+	for (int k = 0; k < NUM_MIRRORS; k++) m_stale[k] = false;
 	m_modelUploaded = false;
 }
 
@@ -226,7 +239,79 @@ void TimeStepDFSPH_B200::pushParameters()
 		p.viscosity = v->getValue<Real>(Viscosity_Standard::VISCOSITY_COEFFICIENT);
 		p.viscosity_boundary = v->getValue<Real>(Viscosity_Standard::VISCOSITY_COEFFICIENT_BOUNDARY);
 	}
+	// set_params synchronises the device and invalidates the solver-loop graphs: only call it when something changed
+	if (m_paramsPushed && std::memcmp(&p, m_lastParams, sizeof(p)) == 0) return;
 	check(m_api->set_params(m_ctx, &p), "dfsph_b200_set_params");
+	std::memcpy(m_lastParams, &p, sizeof(p));
+	m_paramsPushed = true;
+}
+
+void* TimeStepDFSPH_B200::mirror(int which, unsigned int i)
+{
+	if (m_stale[which] && m_ctx)
+	{
+		const unsigned int n = m_uploadedParticles;
+		static const dfsph_b200_field ids[NUM_MIRRORS] = { DFSPH_B200_FIELD_FACTOR, DFSPH_B200_FIELD_DENSITY_ADV, DFSPH_B200_FIELD_KAPPA,
+			DFSPH_B200_FIELD_KAPPA_V, DFSPH_B200_FIELD_PRESSURE_ACCEL };
+		void* dst[NUM_MIRRORS] = { m_factor.data(), m_density_adv.data(), m_pressure_rho2.data(), m_pressure_rho2_V.data(),
+			m_pressureAccel.empty() ? nullptr : &m_pressureAccel[0][0] };
+		if (n > 0) check(m_api->download(m_ctx, ids[which], dst[which], (size_t)n * (which == F_PRESSURE_ACCEL ? 3 : 1) * sizeof(Real), 1), "download field mirror");
+		m_stale[which] = false;
+		m_fieldDownloads++;
+	}
+	switch (which)
+	{
+		case F_FACTOR: return &m_factor[i];
+		case F_DENSITY_ADV: return &m_density_adv[i];
+		case F_KAPPA: return &m_pressure_rho2[i];
+		case F_KAPPA_V: return &m_pressure_rho2_V[i];
+		default: return &m_pressureAccel[i][0];
+	}
+}
+
+void TimeStepDFSPH_B200::downloadField(const std::string& name, Real* dst)
+{
+	Simulation* sim = Simulation::getCurrent();
+	if (!m_ctx || sim->numberOfFluidModels() == 0) return;
+	const unsigned int n = m_uploadedParticles;
+	struct { const char* name; dfsph_b200_field id; int dim; } table[] = {
+		{ "position", DFSPH_B200_FIELD_POSITION, 3 }, { "velocity", DFSPH_B200_FIELD_VELOCITY, 3 }, { "density", DFSPH_B200_FIELD_DENSITY, 1 },
+		{ "factor", DFSPH_B200_FIELD_FACTOR, 1 }, { "advected density", DFSPH_B200_FIELD_DENSITY_ADV, 1 }, { "p / rho^2", DFSPH_B200_FIELD_KAPPA, 1 },
+		{ "p_v / rho^2", DFSPH_B200_FIELD_KAPPA_V, 1 }, { "pressure acceleration", DFSPH_B200_FIELD_PRESSURE_ACCEL, 3 } };
+	for (auto& t : table)
+		if (name == t.name)
+		{
+			if (n > 0) check(m_api->download(m_ctx, t.id, dst, (size_t)n * t.dim * sizeof(Real), 1), "downloadField");
+			m_fieldDownloads++;
+			return;
+		}
+	throw std::runtime_error("TimeStepDFSPH_B200::downloadField: unknown field '" + name + "'");
+}
+
+void TimeStepDFSPH_B200::setHostStateSync(bool b)
+{
+	if (b && !m_hostStateSync) downloadState();
+	m_hostStateSync = b;
+}
+
+void TimeStepDFSPH_B200::downloadState()
+{
+	if (!m_hostStateStale || !m_ctx) return;
+	FluidModel* fm = Simulation::getCurrent()->getFluidModel(0);
+	const unsigned int n = m_uploadedParticles;
+	if (n > 0)
+	{
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_POSITION, &fm->getPosition(0)[0], (size_t)n * 3 * sizeof(Real), 1), "download position");
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_VELOCITY, &fm->getVelocity(0)[0], (size_t)n * 3 * sizeof(Real), 1), "download velocity");
+		check(m_api->download(m_ctx, DFSPH_B200_FIELD_DENSITY, &fm->getDensity(0), (size_t)n * sizeof(Real), 1), "download density");
+	}
+	m_hostStateStale = false;
+}
+
+void TimeStepDFSPH_B200::emittedParticles(FluidModel* model, const unsigned int startIndex)
+{
+	// the device copy no longer matches the model (particle reuse / new active particles): upload it again before the next step
+	m_modelUploaded = false;
 }
 
 void TimeStepDFSPH_B200::uploadModel()
@@ -240,7 +325,14 @@ void TimeStepDFSPH_B200::uploadModel()
 		throw std::runtime_error("TimeStepDFSPH_B200: of the non-pressure forces only viscosityMethod 0 (none) and 1 (Standard viscosity) "
 			"run on the B200 path; set vorticityMethod/dragMethod/surfaceTensionMethod/elasticityMethod to 0 (SURVEY.md H6)");
 
+	// emitters and animation fields change particles on the host between steps (TimeStepDFSPH.cpp:240-241): not on this path
+	if (fm->getEmitterSystem() != nullptr && fm->getEmitterSystem()->numEmitters() > 0)
+		throw std::runtime_error("TimeStepDFSPH_B200: emitters are outside the B200 hot-path scope");
+	if (sim->getAnimationFieldSystem() != nullptr && sim->getAnimationFieldSystem()->numAnimationFields() > 0)
+		throw std::runtime_error("TimeStepDFSPH_B200: animation fields are outside the B200 hot-path scope");
+
 	if (m_ctx) { m_api->destroy(m_ctx); m_ctx = nullptr; }
+	m_paramsPushed = false;
 	dfsph_b200_config cfg;
 	m_api->default_config(&cfg);
 	cfg.particle_radius = sim->getParticleRadius();
@@ -266,6 +358,8 @@ void TimeStepDFSPH_B200::uploadModel()
 			"dfsph_b200_add_boundary");
 	}
 	m_modelUploaded = true;
+	m_uploadedParticles = n;
+	m_hostStateStale = false;
 }
 
 void TimeStepDFSPH_B200::step()
@@ -276,6 +370,8 @@ void TimeStepDFSPH_B200::step()
 	if (sim->numberOfFluidModels() == 0) { tm->setTime(tm->getTime() + h); return; }
 	FluidModel* fm = sim->getFluidModel(0);
 
+	// a changed particle count (reset, state load, emitted particles) means the device copy is out of date
+	if (m_modelUploaded && fm->numActiveParticles() != m_uploadedParticles) m_modelUploaded = false;
 	if (!m_modelUploaded) uploadModel();
 	pushParameters();
 
@@ -283,8 +379,14 @@ void TimeStepDFSPH_B200::step()
 	START_TIMING("DFSPH_B200 step");
 	dfsph_b200_step_stats stats;
 	const unsigned int n = fm->numActiveParticles();
-	check(m_api->step_host(m_ctx, n ? &fm->getPosition(0)[0] : nullptr, n ? &fm->getVelocity(0)[0] : nullptr,
-		n ? &fm->getDensity(0) : nullptr, &stats), "dfsph_b200_step_host");
+	if (m_hostStateSync)
+		check(m_api->step_host(m_ctx, n ? &fm->getPosition(0)[0] : nullptr, n ? &fm->getVelocity(0)[0] : nullptr,
+			n ? &fm->getDensity(0) : nullptr, &stats), "dfsph_b200_step_host");
+	else
+	{
+		check(m_api->step(m_ctx, &stats), "dfsph_b200_step");
+		m_hostStateStale = true;
+	}
 	STOP_TIMING_AVG;
 
 	m_iterations = stats.iterations;
@@ -293,19 +395,17 @@ void TimeStepDFSPH_B200::step()
 	if (m_enableDivergenceSolver)
 		INCREASE_COUNTER("DFSPH - iterationsV", static_cast<Real>(m_iterationsV)); // :497
 
+	// the five DFSPH fields: stale until somebody reads them (mirror()); eager mode fetches them now
+	for (int k = 0; k < NUM_MIRRORS; k++) m_stale[k] = true;
 	if (m_syncAllFields && n > 0)
-	{
-		check(m_api->download(m_ctx, DFSPH_B200_FIELD_FACTOR, m_factor.data(), n * sizeof(Real), 1), "download factor");
-		check(m_api->download(m_ctx, DFSPH_B200_FIELD_DENSITY_ADV, m_density_adv.data(), n * sizeof(Real), 1), "download advected density");
-		check(m_api->download(m_ctx, DFSPH_B200_FIELD_KAPPA, m_pressure_rho2.data(), n * sizeof(Real), 1), "download p / rho^2");
-		check(m_api->download(m_ctx, DFSPH_B200_FIELD_KAPPA_V, m_pressure_rho2_V.data(), n * sizeof(Real), 1), "download p_v / rho^2");
-		check(m_api->download(m_ctx, DFSPH_B200_FIELD_PRESSURE_ACCEL, &m_pressureAccel[0][0], n * 3 * sizeof(Real), 1), "download pressure acceleration");
-	}
+		for (int k = 0; k < NUM_MIRRORS; k++) mirror(k, 0);
 
 	// Simulation::updateTimeStepSize ran on the device (Simulation.cpp:395-493); publish its result, then advance time
 	// with the step's initial h exactly like TimeStepDFSPH::step (:248)
 	tm->setTimeStepSize(static_cast<Real>(stats.time_step_size));
 	tm->setTime(tm->getTime() + h);
+	// the device already holds this step size: the next pushParameters must not see it as a change
+	reinterpret_cast<dfsph_b200_params*>(m_lastParams)->time_step_size = static_cast<Real>(stats.time_step_size);
 }
 
 void TimeStepDFSPH_B200::downloadNeighbors(unsigned int other, std::vector<unsigned int>& offsets, std::vector<unsigned int>& indices)
@@ -315,7 +415,7 @@ void TimeStepDFSPH_B200::downloadNeighbors(unsigned int other, std::vector<unsig
 	const unsigned int n = fm->numActiveParticles();
 	if (!m_modelUploaded) uploadModel();
 	// host positions are authoritative: search exactly what the host sees
-	if (n > 0) check(m_api->upload(m_ctx, DFSPH_B200_FIELD_POSITION, &fm->getPosition(0)[0], n * 3 * sizeof(Real), 1), "upload position");
+	if (n > 0 && !m_hostStateStale) check(m_api->upload(m_ctx, DFSPH_B200_FIELD_POSITION, &fm->getPosition(0)[0], n * 3 * sizeof(Real), 1), "upload position");
 	std::vector<unsigned int> counts(n), ids(n);
 	std::vector<uint64_t> off(n + 1, 0);
 	check(m_api->neighbors(m_ctx, (int)other, counts.data(), nullptr, nullptr, 0), "dfsph_b200_neighbors");
@@ -337,36 +437,115 @@ void TimeStepDFSPH_B200::downloadNeighbors(unsigned int other, std::vector<unsig
 	}
 }
 
+const std::vector<unsigned int> NeighborhoodSearch_B200::s_empty;
+
+unsigned int NeighborhoodSearch_B200::add_point_set(Real const* x, std::size_t n, bool is_dynamic, bool search_neighbors, bool find_neighbors, void* user_data)
+{
+	PointSet ps;
+	ps.m_ns = this; ps.m_index = (unsigned int)m_sets.size(); ps.m_x = x; ps.m_n = n;
+	ps.m_dynamic = is_dynamic; ps.m_search = search_neighbors; ps.m_find = find_neighbors; ps.m_user = user_data;
+	m_sets.push_back(ps);
+	for (auto& s : m_sets) s.m_ns = this;
+	// CompactNSearch: a new set searches / is found according to its flags against every existing set
+	const std::size_t k = m_sets.size();
+	m_active.resize(k);
+	for (std::size_t i = 0; i < k; i++) m_active[i].resize(k, false);
+	for (std::size_t i = 0; i < k; i++)
+	{
+		m_active[i][k - 1] = m_sets[i].m_search && find_neighbors;
+		m_active[k - 1][i] = search_neighbors && m_sets[i].m_find;
+	}
+	m_sortTable.resize(k);
+	return ps.m_index;
+}
+
+void NeighborhoodSearch_B200::resize_point_set(unsigned int i, Real const* x, std::size_t n)
+{
+	m_sets[i].m_x = x; m_sets[i].m_n = n;
+}
+
+void NeighborhoodSearch_B200::set_active(bool active)
+{
+	for (auto& row : m_active) for (std::size_t j = 0; j < row.size(); j++) row[j] = active;
+}
+
+void NeighborhoodSearch_B200::set_active(unsigned int i, bool search_neighbors, bool find_neighbors)
+{
+	for (std::size_t j = 0; j < m_active.size(); j++) { m_active[i][j] = search_neighbors; m_active[j][i] = find_neighbors; }
+}
+
+void NeighborhoodSearch_B200::set_active(unsigned int i, unsigned int j, bool active)
+{
+	m_active[i][j] = active;
+}
+
 void NeighborhoodSearch_B200::find_neighbors()
 {
 	Simulation* sim = Simulation::getCurrent();
+	const unsigned int nsets = 1 + sim->numberOfBoundaryModels();
+	if (m_sets.empty())
+	{
+		// used without add_point_set (round-1 style): mirror the Simulation's sets with the reference's flags
+		FluidModel* fm = sim->getFluidModel(0);
+		add_point_set(&fm->getPosition(0)[0], fm->numActiveParticles(), true, true, true, fm);
+		for (unsigned int b = 0; b < sim->numberOfBoundaryModels(); b++)
+		{
+			BoundaryModel_Akinci2012* bm = static_cast<BoundaryModel_Akinci2012*>(sim->getBoundaryModel(b));
+			add_point_set(&bm->getPosition(0)[0], bm->numberOfParticles(), false, false, true, bm);
+		}
+	}
+	std::vector<unsigned int> off, idx;
+	m_off.assign(nsets, std::vector<unsigned int>());
+	m_idx.assign(nsets, std::vector<unsigned int>());
 	m_ts.downloadNeighbors(0, m_off[0], m_idx[0]);
-	m_ts.downloadNeighbors(1, m_off[1], m_idx[1]);
-	m_bodyStart.assign(1, 0u);
+	m_ts.downloadNeighbors(1, off, idx);
+	// split the concatenated boundary lists into one CSR per boundary model (local indices)
+	std::vector<unsigned int> bodyStart(1, 0u);
 	for (unsigned int b = 0; b < sim->numberOfBoundaryModels(); b++)
-		m_bodyStart.push_back(m_bodyStart.back() + static_cast<BoundaryModel_Akinci2012*>(sim->getBoundaryModel(b))->numberOfParticles());
+		bodyStart.push_back(bodyStart.back() + static_cast<BoundaryModel_Akinci2012*>(sim->getBoundaryModel(b))->numberOfParticles());
+	const std::size_t n = off.empty() ? 0 : off.size() - 1;
+	for (unsigned int b = 0; b + 1 < nsets; b++)
+	{
+		std::vector<unsigned int>& o = m_off[b + 1]; std::vector<unsigned int>& x = m_idx[b + 1];
+		o.assign(n + 1, 0u);
+		for (std::size_t i = 0; i < n; i++)
+		{
+			for (unsigned int k = off[i]; k < off[i + 1]; k++)
+				if (idx[k] >= bodyStart[b] && idx[k] < bodyStart[b + 1]) x.push_back(idx[k] - bodyStart[b]);
+			o[i + 1] = (unsigned int)x.size();
+		}
+	}
 }
 
-std::vector<unsigned int> NeighborhoodSearch_B200::neighbor_list(unsigned int ps, unsigned int i) const
+void NeighborhoodSearch_B200::z_sort()
 {
-	std::vector<unsigned int> out;
-	if (ps == 0) { out.assign(m_idx[0].begin() + m_off[0][i], m_idx[0].begin() + m_off[0][i + 1]); return out; }
-	const unsigned int lo = m_bodyStart[ps - 1], hi = m_bodyStart[ps];
-	for (unsigned int k = m_off[1][i]; k < m_off[1][i + 1]; k++)
-		if (m_idx[1][k] >= lo && m_idx[1][k] < hi) out.push_back(m_idx[1][k] - lo);
-	return out;
+	m_ts.downloadSortTable(m_sortTable.empty() ? (m_sortTable.resize(1), m_sortTable[0]) : m_sortTable[0]);
 }
 
-unsigned int NeighborhoodSearch_B200::n_neighbors(unsigned int ps, unsigned int i) const
+unsigned int NeighborhoodSearch_B200::n_neighbors_of(unsigned int a, unsigned int set, unsigned int i) const
 {
-	if (ps == 0) return m_off[0][i + 1] - m_off[0][i];
-	return (unsigned int)neighbor_list(ps, i).size();
+	if (a != 0 || set >= m_off.size() || !is_active(a, set) || m_off[set].empty()) return 0;
+	return m_off[set][i + 1] - m_off[set][i];
 }
 
-unsigned int NeighborhoodSearch_B200::neighbor(unsigned int ps, unsigned int i, unsigned int k) const
+unsigned int NeighborhoodSearch_B200::neighbor_of(unsigned int a, unsigned int set, unsigned int i, unsigned int k) const
 {
-	if (ps == 0) return m_idx[0][m_off[0][i] + k];
-	return neighbor_list(ps, i)[k];
+	return m_idx[set][m_off[set][i] + k];
+}
+
+const std::vector<unsigned int>& NeighborhoodSearch_B200::list_of(unsigned int a, unsigned int set, unsigned int i) const
+{
+	if (n_neighbors_of(a, set, i) == 0) return s_empty;
+	m_scratch.assign(m_idx[set].begin() + m_off[set][i], m_idx[set].begin() + m_off[set][i + 1]);
+	return m_scratch;
+}
+
+void TimeStepDFSPH_B200::downloadSortTable(std::vector<unsigned int>& table)
+{
+	// device row r holds host particle id[r]: exactly the table PointSet::sort_field applies (new[r] = old[table[r]])
+	const unsigned int n = m_uploadedParticles;
+	table.assign(n, 0u);
+	if (m_ctx && n > 0) check(m_api->download(m_ctx, DFSPH_B200_FIELD_ID, table.data(), (size_t)n * sizeof(unsigned int), 0), "download id");
 }
 
 void Simulation_B200::useB200Solver(const std::string& libraryPath)

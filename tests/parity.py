@@ -69,19 +69,16 @@ def conditioned_errors(name, dev_f, ref_f, ref, h):
 
 
 def neighbor_sets_by_id(counts, offsets, idx, row_ids, col_ids=None):
-    """CSR in array order -> dict-free canonical form: (ids sorted, per-id sorted neighbour id arrays concatenated)."""
-    n = len(counts)
-    cols = idx if col_ids is None else col_ids[idx]
-    order = np.argsort(row_ids, kind="stable")
-    out_counts = counts[order]
-    out = np.empty(len(cols), dtype=np.uint32)
-    pos = 0
-    for r in order:
-        s, e = int(offsets[r]), int(offsets[r + 1])
-        seg = np.sort(cols[s:e])
-        out[pos:pos + (e - s)] = seg
-        pos += e - s
-    return out_counts, out
+    """CSR in array order -> canonical form: (counts ordered by particle id, per-id ascending neighbour ids concatenated)."""
+    counts = np.asarray(counts)
+    cols = np.asarray(idx if col_ids is None else np.asarray(col_ids)[idx], dtype=np.uint32)
+    rows = np.repeat(np.asarray(row_ids, dtype=np.uint32), counts)      # CSR rows are contiguous: offsets = cumsum(counts)
+    order = np.lexsort((cols, rows))
+    out_counts = np.zeros(len(counts), dtype=counts.dtype)
+    out_counts[np.asarray(row_ids)] = counts
+    if len(row_ids) and np.array_equal(np.sort(np.asarray(row_ids)), np.arange(len(row_ids))):
+        return out_counts, cols[order]
+    return counts[np.argsort(row_ids, kind="stable")], cols[order]
 
 
 def sync_state(ref, dev):
@@ -93,9 +90,16 @@ def sync_state(ref, dev):
     dev.setValue("timeStepSize", ref.h)
 
 
-def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, check_neighbors=True, grad_kernel=None, **params):
+def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, check_neighbors=True, grad_kernel=None, preroll=0,
+                 collect=None, **params):
     """Run `steps` steps on the oracle and on the device from identical input states; compare every per-step field,
-    the iteration counts, the new time step size and (first step) the neighbour sets.  Returns a result dict."""
+    the iteration counts, the new time step size and (first step) the neighbour sets.  Returns a result dict.
+
+    preroll: the oracle first advances this many steps on its own (the device then starts from the oracle's state), so
+    that the compared steps lie in a later phase of the scene (more solver iterations per step).
+    collect: optional callable(step, ref, dev, stats) -> dict, stored per step under "extra" (run statistics).
+    Where a conditioned measure replaces the scale-relative error of kappa / the pressure acceleration, the step record
+    keeps both numbers under "conditioned" and the result counts the fallbacks in "conditioned_fallbacks"."""
     from splishsplash_b200.solver import build_b200_scene
     tol = TOL[precision] if tol is None else tol
     ref, kind = make_oracle(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params)
@@ -141,6 +145,8 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
                     same = same and sameb
                 if not same:
                     res["ok"] = False
+            if preroll:
+                ref.step(int(preroll))
             for s in range(steps):
                 if resync or s == 0:
                     sync_state(ref, dev)
@@ -155,6 +161,7 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
                         ce = conditioned_errors(name, df, rf, ref, ref.h)
                         if ce is not None:
                             rec.setdefault("conditioned", {})[name] = (e, ce)
+                            res["conditioned_fallbacks"] = res.get("conditioned_fallbacks", 0) + 1
                             e = min(e, ce)
                     rec["err"][name] = e
                     res["max_err"][name] = max(res["max_err"].get(name, 0.0), e)
@@ -164,6 +171,8 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
                     res["ok"] = False
                 if abs(rec["ref_h"] - rec["dev_h"]) > tol * abs(rec["ref_h"]):
                     res["ok"] = False
+                if collect is not None:
+                    rec["extra"] = collect(s, ref, dev, st)
                 res["steps"].append(rec)
         finally:
             dev.close()
@@ -172,5 +181,6 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
     worst = max(res["max_err"].items(), key=lambda kv: kv[1]) if res["max_err"] else ("-", 0.0)
     res["summary"] = (f"oracle={kind} N={len(scene['fluid_x'])} steps={steps} worst={worst[0]}:{worst[1]:.3e} "
                       f"iters={[(r['ref_iter'], r['dev_iter']) for r in res['steps']]} "
-                      f"nbr_equal={res.get('neighbors_fluid_equal')}/{res.get('neighbors_boundary_equal')} ok={res['ok']}")
+                      f"nbr_equal={res.get('neighbors_fluid_equal')}/{res.get('neighbors_boundary_equal')} "
+                      f"conditioned_fallbacks={res.get('conditioned_fallbacks', 0)} ok={res['ok']}")
     return res

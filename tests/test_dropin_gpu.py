@@ -107,3 +107,79 @@ def test_neighborhood_search_facade_matches_reference_lists():
             assert cs.value == want[pid][1]
     finally:
         dev.destroy()
+
+
+def test_lazy_field_mirrors_and_bulk_accessor():
+    """a step downloads none of the five DFSPH fields; the first getFct(i) of a field (the way the
+    reference's state writer and exporters read, SimulatorBase.cpp:2094-2123) triggers ONE bulk download of that field;
+    downloadField() is the explicit bulk accessor."""
+    import ctypes as C
+    prec = "f64"
+    if not refsim.ref_available(prec):
+        pytest.skip("oracle/_ref not present")
+    sc = scenes.dam_break("small", dtype=dtype_of(prec))
+    dev = refsim.build_ref_scene(sc, prec, kernel=4, b200=True)
+    try:
+        L = dev.lib
+        L.ref_b200_download_field.argtypes = [C.c_char_p, C.c_void_p]
+        dev.step(3)
+        assert L.ref_b200_field_downloads() == 0                    # nobody read a DFSPH field
+        factor = dev.field_by_id("factor")                          # per-particle getFct reads through the reference's FieldDescription
+        assert L.ref_b200_field_downloads() == 1
+        dev.field_by_id("factor")
+        assert L.ref_b200_field_downloads() == 1                    # still current: no second copy
+        kappa = dev.field_by_id("p / rho^2")
+        assert L.ref_b200_field_downloads() == 2
+        dev.step(1)
+        assert L.ref_b200_field_downloads() == 2
+        n = dev.num_particles()
+        bulk = np.empty(n, dtype=np.float64)
+        assert L.ref_b200_download_field(b"factor", bulk.ctypes.data) == 0
+        assert L.ref_b200_field_downloads() == 3
+        assert np.array_equal(bulk, dev.field("factor"))            # same values as the per-particle path (host array order)
+        assert factor.shape == kappa.shape == (n,)
+        assert L.ref_b200_download_field(b"no such field", bulk.ctypes.data) == -2
+    finally:
+        dev.destroy()
+
+
+def test_device_resident_state_matches_host_synchronised_run():
+    """setHostStateSync(false): x, v stay on the device between steps; downloadState() brings FluidModel's arrays up to
+    date.  The result is bitwise the host-synchronised run (the same kernels on the same data)."""
+    prec = "f64"
+    if not refsim.ref_available(prec):
+        pytest.skip("oracle/_ref not present")
+    sc = scenes.dam_break("small", dtype=dtype_of(prec))
+    out = {}
+    for mode in (1, 0):
+        dev = refsim.build_ref_scene(sc, prec, kernel=4, b200=True)
+        try:
+            dev.step(1)                                              # uploads the model
+            assert dev.lib.ref_b200_set_host_sync(mode) == 0
+            dev.step(5)
+            if mode == 0:
+                stale = dev.field_by_id("position")
+                assert dev.lib.ref_b200_download_state() == 0
+                assert not np.array_equal(stale, dev.field_by_id("position"))   # the host copy really was behind
+            out[mode] = (dev.field_by_id("position"), dev.field_by_id("velocity"), dev.field_by_id("density"), dev.iterations, dev.time)
+        finally:
+            dev.destroy()
+    for a, b in zip(out[0][:3], out[1][:3]):
+        assert np.array_equal(a, b)
+    assert out[0][3:] == out[1][3:]
+
+
+def test_compactnsearch_facade_surface():
+    """add_point_set / set_active / find_neighbors / z_sort / sort_field of NeighborhoodSearch_B200 used the way the
+    reference uses CompactNSearch (SURVEY.md B.1); the checks live in oracle/ref_driver.cpp::ref_b200_facade_selftest."""
+    prec = "f64"
+    if not refsim.ref_available(prec):
+        pytest.skip("oracle/_ref not present")
+    sc = scenes.dam_break("small", dtype=dtype_of(prec))
+    dev = refsim.build_ref_scene(sc, prec, kernel=4, b200=True, enableZSort=0)
+    try:
+        dev.step(2)
+        rc = dev.lib.ref_b200_facade_selftest()
+        assert rc == 0, (rc, dev.lib.ref_last_error())
+    finally:
+        dev.destroy()
