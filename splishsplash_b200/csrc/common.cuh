@@ -100,6 +100,7 @@ struct GridDesc {
     int nby, nbz;           // blocks per axis (y, z)
     unsigned num_keys;      // table entries: blocks * DFSPH_ENTRIES_PER_BLOCK (the dump cell of the slab sort sits behind them)
     const unsigned* block_rank;   // [nbx*nby*nbz] position of each block along the z-order curve over blocks
+    const unsigned* block_of_rank;   // inverse of block_rank: linear block index (bx nby + by) nbz + bz of the r-th block of the curve
 };
 
 __host__ __device__ __forceinline__ unsigned spread3(unsigned v)   // 3 bits -> bits 0,3,6

@@ -43,7 +43,10 @@ struct dfsph_b200_ctx {
     Real4 *acc = nullptr, *bgrad = nullptr;
     Real *density = nullptr, *factor = nullptr, *density_adv = nullptr;
     unsigned *nnbr = nullptr, *cnt_f = nullptr, *cnt_b = nullptr, *tab_f = nullptr, *tab_b = nullptr, *tcnt_f = nullptr, *tcnt_b = nullptr;
-    unsigned *cell_key = nullptr, *cell_rank = nullptr, *cell_fine = nullptr, *sorted_idx = nullptr, *block_rank = nullptr;
+    unsigned *cell_key = nullptr, *cell_rank = nullptr, *cell_fine = nullptr, *sorted_idx = nullptr, *block_rank = nullptr, *block_of_rank = nullptr;
+    unsigned nblocks = 0, nbx = 0;
+    unsigned char* bpart_near = nullptr;   // per block part: boundary points in reach (k_mark_boundary_parts)
+    bool tile_build = true, tile_attr_set = false;   // fluid-fluid table from shared-memory tiles (DFSPH_B200_TILE_BUILD=0: one-thread walk)
     unsigned *cell_count = nullptr, *cell_start = nullptr, *scan_partial = nullptr;
     unsigned keys_cap = 0, scratch_cap = 0;
     bool tables_valid = false;   // neighbour table matches pos[cur_pos]
@@ -379,6 +382,7 @@ int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out)
     c->cfg = *cfg;
     dfsph_b200_default_params(&c->par);
     c->use_graph = getenv("DFSPH_B200_NO_GRAPH") == nullptr;
+    if (const char* e = getenv("DFSPH_B200_TILE_BUILD")) c->tile_build = e[0] != '0';
     c->Kf = cfg->max_fluid_neighbors > 0 ? (unsigned)cfg->max_fluid_neighbors : 64u;
     c->Kb = cfg->max_boundary_neighbors > 0 ? (unsigned)cfg->max_boundary_neighbors : 64u;
     c->Kf = (c->Kf + DFSPH_PAD - 1u) & ~(DFSPH_PAD - 1u);
@@ -411,7 +415,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
     cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b); cudaFree(c->tcnt_f); cudaFree(c->tcnt_b);
-    cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
+    cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->block_of_rank); cudaFree(c->bpart_near); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
     cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start); cudaFree(c->bnear);
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
     cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->send_l); cudaFree(c->send_r);
@@ -537,6 +541,12 @@ static int setup_grid(dfsph_b200_ctx* c)
         if (dev_alloc(c, &c->block_rank, nblocks)) return DFSPH_B200_ERR_CUDA;
         CUDA_TRY(c, cudaMemcpy(c->block_rank, rank.data(), (size_t)nblocks * sizeof(unsigned), cudaMemcpyHostToDevice));
         g.block_rank = c->block_rank;
+        std::vector<unsigned> inv(nblocks);
+        for (unsigned r = 0; r < nblocks; ++r) inv[r] = codes[r].second;
+        if (dev_alloc(c, &c->block_of_rank, nblocks)) return DFSPH_B200_ERR_CUDA;
+        CUDA_TRY(c, cudaMemcpy(c->block_of_rank, inv.data(), (size_t)nblocks * sizeof(unsigned), cudaMemcpyHostToDevice));
+        g.block_of_rank = c->block_of_rank;
+        c->nblocks = nblocks; c->nbx = nbx;
     }
     c->grid = g;
     const unsigned nfine = g.num_keys;   // table entries (+ the dump cell)
@@ -615,6 +625,11 @@ static int finalize_boundary(dfsph_b200_ctx* c)
         const size_t ncell = (size_t)c->grid.nx * c->grid.ny * c->grid.nz;
         if (dev_alloc(c, &c->bnear, ncell)) rc = DFSPH_B200_ERR_CUDA;
         else if (cudaMemsetAsync(c->bnear, 0, ncell, c->stream) != cudaSuccess) rc = DFSPH_B200_ERR_CUDA;
+    }
+    if (rc == 0) {
+        const unsigned nparts = c->nblocks * TB_PARTS;
+        if (dev_alloc(c, &c->bpart_near, nparts)) rc = DFSPH_B200_ERR_CUDA;
+        else k_mark_boundary_parts<<<div_up(nparts, 4), 128, 0, c->stream>>>(c->grid, c->nbx, nparts, c->bcell_start, c->bpart_near);
     }
     if (rc == 0 && nb > 0) {
         k_mark_boundary_cells<<<div_up(nb, DFSPH_BLOCK), DFSPH_BLOCK, 0, c->stream>>>(nb, c->grid, tmp, c->bnear);
@@ -1146,7 +1161,21 @@ static int run_search(dfsph_b200_ctx* c)
     }
     if (n > 0) {
         ProfScope ps(c, DFSPH_B200_PROF_BUILD);
-        k_build_neighbors<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
+        if (c->tile_build) {
+            if (!c->tile_attr_set) {
+                CUDA_TRY(c, cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM_BYTES));
+                c->tile_attr_set = true;
+            }
+            k_build_tiles<<<c->nblocks * TB_PARTS, DFSPH_TB_THREADS, TB_SMEM_BYTES, st>>>(c->grid, c->nbx, c->sph.R2, n, c->multi ? 0 : 1,
+                c->pos[c->cur_pos], c->cell_start, c->tab_f, c->Kf, c->cnt_f, c->tcnt_f,
+                c->bpos, c->bcell_start, c->nb, c->tab_b, c->Kb, c->cnt_b, c->tcnt_b, n + c->ng, c->bpart_near, c->ctrl);
+            k_build_neighbors<false><<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
+                c->bpos, c->bcell_start, c->nb, c->bnear, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
+                c->ng, c->gcell_start, c->sorted_idx, c->slab_axis,
+                c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300);
+            c->launches++;
+        } else
+        k_build_neighbors<true><<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
             c->bpos, c->bcell_start, c->nb, c->bnear, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
             c->ng, c->gcell_start, c->sorted_idx, c->slab_axis,
             c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300);

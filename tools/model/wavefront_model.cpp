@@ -19,6 +19,7 @@ int main(int argc, char** argv)
     const int order = argc > 3 ? atoi(argv[3]) : 0;         // 0: 8^3 blocks, x fastest in block; 1: Morton in block
     const int cluster = argc > 4 ? atoi(argv[4]) : 1;       // particles per lane (1 or 2 or 4)
     const int sortlist = argc > 5 ? atoi(argv[5]) : 0;      // 1: lists sorted by address
+    const int split = argc > 6 ? atoi(argv[6]) : 1;         // lanes per particle (1, 2, 4, 8): lane s of particle p reads entries k*split + s
     const float d = 0.05f, R = 0.1f, S = R * 1.00001f;
     std::mt19937 rng(1);
     std::uniform_real_distribution<float> U(-jitter * d, jitter * d);
@@ -97,6 +98,25 @@ int main(int argc, char** argv)
         }
         if (sortlist || cluster > 1) std::sort(u.begin(), u.end());
         ll[l] = u;
+    }
+    if (split > 1) {
+        // `split` lanes per particle: a warp holds 32/split particles, step k of lane (p, s) reads entry k*split + s
+        const int PW = 32 / split;
+        double wsteps = 0, lines = 0, entries = 0;
+        for (int t = 0; t < (N + PW - 1) / PW; ++t) {
+            size_t mx = 0;
+            for (int i = t * PW; i < std::min(N, t * PW + PW); ++i) mx = std::max(mx, (ll[i].size() + split - 1) / split);
+            wsteps += mx;
+            for (size_t k = 0; k < mx; ++k) {
+                std::map<int, int> wl;
+                for (int i = t * PW; i < std::min(N, t * PW + PW); ++i)
+                    for (int s2 = 0; s2 < split; ++s2) { const size_t e = k * split + s2; const int j = e < ll[i].size() ? ll[i][e] : N; wl[j / 8]++; if (e < ll[i].size()) entries += 1; }
+                for (auto& kv : wl) lines += (kv.second + 7) / 8;
+            }
+        }
+        printf("N=%d order=%d split=%d sorted=%d jitter=%.2f: neighbours/particle %.2f, warp-steps/particle %.4f (x32 = %.1f slots/particle), lines per warp-gather %.2f, lines/particle %.3f\n",
+               N, order, split, sortlist, jitter, entries / N, wsteps / N, 32.0 * wsteps / N, lines / wsteps, lines / N);
+        return 0;
     }
     // per warp tile: padded length = max rounded to 4; count lines per quarter-warp
     double steps = 0, wf = 0, slots = 0, wf_warp = 0;
