@@ -48,6 +48,11 @@ struct dfsph_b200_ctx {
     unsigned char* bpart_near = nullptr;   // per block part: boundary points in reach (k_mark_boundary_parts)
     bool tile_build = true, tile_attr_set = false;   // fluid-fluid table from shared-memory tiles (DFSPH_B200_TILE_BUILD=0: one-thread walk)
     unsigned *cell_count = nullptr, *cell_start = nullptr, *scan_partial = nullptr;
+    unsigned long long* scan_status = nullptr;   // look-back scan: one word per chunk, tagged with scan_epoch
+    unsigned* scan_ticket = nullptr;
+    unsigned scan_epoch = 0;
+    bool fused_reorder = true;      // single GPU: k_fix_reorder instead of k_cell_fix_order + k_reorder (DFSPH_B200_FUSED_REORDER=0)
+    bool scan_single_pass = true;   // DFSPH_B200_SCAN=3: the three-kernel scan
     unsigned keys_cap = 0, scratch_cap = 0;
     bool tables_valid = false;   // neighbour table matches pos[cur_pos]
     cudaTextureObject_t acc_tex = 0, pos_tex[2] = {0, 0}, vel_tex[2] = {0, 0};
@@ -383,6 +388,8 @@ int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out)
     dfsph_b200_default_params(&c->par);
     c->use_graph = getenv("DFSPH_B200_NO_GRAPH") == nullptr;
     if (const char* e = getenv("DFSPH_B200_TILE_BUILD")) c->tile_build = e[0] != '0';
+    if (const char* e = getenv("DFSPH_B200_SCAN")) c->scan_single_pass = e[0] != '3';
+    if (const char* e = getenv("DFSPH_B200_FUSED_REORDER")) c->fused_reorder = e[0] != '0';
     c->Kf = cfg->max_fluid_neighbors > 0 ? (unsigned)cfg->max_fluid_neighbors : 64u;
     c->Kb = cfg->max_boundary_neighbors > 0 ? (unsigned)cfg->max_boundary_neighbors : 64u;
     c->Kf = (c->Kf + DFSPH_PAD - 1u) & ~(DFSPH_PAD - 1u);
@@ -416,7 +423,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     cudaFree(c->acc); cudaFree(c->bgrad); cudaFree(c->density); cudaFree(c->factor); cudaFree(c->density_adv);
     cudaFree(c->nnbr); cudaFree(c->cnt_f); cudaFree(c->cnt_b); cudaFree(c->tab_f); cudaFree(c->tab_b); cudaFree(c->tcnt_f); cudaFree(c->tcnt_b);
     cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->block_of_rank); cudaFree(c->bpart_near); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
-    cudaFree(c->scan_partial); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start); cudaFree(c->bnear);
+    cudaFree(c->scan_partial); cudaFree(c->scan_status); cudaFree(c->scan_ticket); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start); cudaFree(c->bnear);
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
     cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->send_l); cudaFree(c->send_r);
     cudaFree(c->send_l2); cudaFree(c->send_r2); cudaFree(c->aux_sl); cudaFree(c->aux_sr); cudaFree(c->aux_rl); cudaFree(c->aux_rr);
@@ -556,6 +563,10 @@ static int setup_grid(dfsph_b200_ctx* c)
         if (dev_alloc(c, &c->bcell_start, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
         if (c->multi && dev_alloc(c, &c->gcell_start, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->scan_partial, div_up(nfine + 1, SCAN_CHUNK) + 8)) return DFSPH_B200_ERR_CUDA;
+        if (dev_alloc(c, &c->scan_status, div_up(nfine + 1, SCAN1_CHUNK) + 8)) return DFSPH_B200_ERR_CUDA;
+        CUDA_TRY(c, cudaMemsetAsync(c->scan_status, 0, ((size_t)div_up(nfine + 1, SCAN1_CHUNK) + 8) * sizeof(unsigned long long), c->stream));
+        if (!c->scan_ticket && dev_alloc(c, &c->scan_ticket, 1)) return DFSPH_B200_ERR_CUDA;
+        c->scan_epoch = 0;
         c->keys_cap = nfine + 1;
     }
     c->grid_valid = true;
@@ -566,7 +577,8 @@ static int setup_grid(dfsph_b200_ctx* c)
 
 // counting sort of `n` points at `pos` into the cell table `cell_start_out`; leaves the permutation in sorted_idx
 // slab: particles outside the context's slab are filed under the dump key num_keys (multi-GPU migration)
-static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* cell_start_out, bool slab = false)
+// fix = false: the caller orders the entries itself (k_fix_reorder)
+static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* cell_start_out, bool slab = false, bool fix = true)
 {
     const GridDesc& g = c->grid;
     cudaStream_t st = c->stream;
@@ -579,14 +591,24 @@ static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* 
         c->launches++;
     }
     const unsigned nparts = div_up(nk, SCAN_CHUNK);
+    if (c->scan_single_pass) {
+        if (++c->scan_epoch >= (1u << 30)) {   // the tag has 30 bits: start over with a clean status array
+            CUDA_TRY(c, cudaMemsetAsync(c->scan_status, 0, ((size_t)div_up(nk, SCAN1_CHUNK) + 8) * sizeof(unsigned long long), st));
+            c->scan_epoch = 1;
+        }
+        CUDA_TRY(c, cudaMemsetAsync(c->scan_ticket, 0, sizeof(unsigned), st));
+        k_scan_lookback<<<div_up(nk, SCAN1_CHUNK), SCAN_BLOCK, 0, st>>>(c->cell_count, nk, cell_start_out, c->scan_status, c->scan_ticket, c->scan_epoch);
+        c->launches += 1;
+    } else {
     k_scan_partials<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, nk, c->scan_partial);
     k_scan_spine<<<1, SCAN_BLOCK, 0, st>>>(c->scan_partial, nparts);
     k_scan_apply<<<nparts, SCAN_BLOCK, 0, st>>>(c->cell_count, nk, c->scan_partial, nparts, cell_start_out);
     c->launches += 3;
+    }
     if (n > 0) {
         k_cell_scatter<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(c->cell_key, c->cell_rank, n, cell_start_out, c->sorted_idx);
-        k_cell_fix_order<<<div_up(nk, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(cell_start_out, nk, c->cell_fine, c->sorted_idx);
-        c->launches += 2;
+        if (fix) k_cell_fix_order<<<div_up(nk, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(cell_start_out, nk, c->cell_fine, c->sorted_idx);
+        c->launches += fix ? 2 : 1;
     }
     CUDA_TRY(c, cudaGetLastError());
     return 0;
@@ -1106,7 +1128,7 @@ static int run_search(dfsph_b200_ctx* c)
         c->n = n;
     } else {
         ProfScope ps(c, DFSPH_B200_PROF_SORT);
-        rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start);
+        rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start, false, !c->fused_reorder);
         if (rc) return rc;
     }
     c->ng = c->ng_l = c->ng_r = 0;
@@ -1114,7 +1136,11 @@ static int run_search(dfsph_b200_ctx* c)
         const int src = c->cur, dst = 1 - c->cur;
         const int psrc = c->cur_pos, pdst = 1 - c->cur_pos;
         ProfScope ps(c, DFSPH_B200_PROF_SORT);
-        if (n > 0) k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
+        if (n > 0 && !c->multi && c->fused_reorder)
+            k_fix_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->cell_key, c->cell_fine, c->cell_start, c->cell_rank,
+                c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src], c->id[src], c->state[src],
+                c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc);
+        else if (n > 0) k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
             c->id[src], c->state[src], c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc);
         c->cur = dst; c->cur_pos = pdst;
         c->launches++;

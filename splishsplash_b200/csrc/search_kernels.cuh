@@ -101,6 +101,82 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const unsigned* __res
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = partial[nparts];
 }
 
+// Single-pass exclusive scan (chained scan with decoupled look-back): every block publishes its chunk total, then the
+// inclusive prefix up to its end, in one 64-bit word per chunk -- (epoch, state, value) -- and the blocks are numbered by an
+// atomic ticket in the order they start, so a block only ever waits for blocks that are already running.  One read and one
+// write of the array instead of two reads, one write and a serial spine kernel (0.31 -> 0.09 ms for the 50 M-entry table
+// of the 10 M-particle scene).  `epoch` must differ from call to call on the same `status` array (no reset needed).
+#define SCAN1_ITEMS 16
+#define SCAN1_CHUNK (SCAN1_ITEMS * SCAN_BLOCK)
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_lookback(const unsigned* __restrict__ in, unsigned n, unsigned* __restrict__ out,
+                                                                unsigned long long* status, unsigned* ticket, unsigned epoch)
+{
+    __shared__ unsigned s_bid, s_prefix;
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const unsigned base = bid * SCAN1_CHUNK + threadIdx.x * SCAN1_ITEMS;
+    unsigned v[SCAN1_ITEMS];
+    unsigned s = 0;
+    if (base + SCAN1_ITEMS <= n) {
+#pragma unroll
+        for (unsigned k = 0; k < SCAN1_ITEMS; k += 4) {
+            const uint4 a = *reinterpret_cast<const uint4*>(in + base + k);
+            v[k] = a.x; v[k + 1] = a.y; v[k + 2] = a.z; v[k + 3] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (unsigned k = 0; k < SCAN1_ITEMS; ++k) v[k] = base + k < n ? in[base + k] : 0u;
+    }
+#pragma unroll
+    for (unsigned k = 0; k < SCAN1_ITEMS; ++k) s += v[k];
+    unsigned total;
+    unsigned ex = block_excl_scan(s, &total);
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    if (threadIdx.x < 32) {
+        // warp 0 looks back 32 chunks at a time
+        const unsigned lane = threadIdx.x;
+        unsigned prefix = 0u;
+        if (bid == 0u) {
+            if (lane == 0u) atomicExch(status, tag | (2ull << 32) | total);
+        } else {
+            if (lane == 0u) atomicExch(status + bid, tag | (1ull << 32) | total);      // chunk total is known
+            int j0 = (int)bid - 1;                                                      // lane l inspects chunk j0 - l
+            while (true) {
+                const int j = j0 - (int)lane;
+                unsigned long long st = tag | (2ull << 32);                              // before chunk 0: an inclusive prefix of 0
+                if (j >= 0) do { st = *reinterpret_cast<volatile unsigned long long*>(status + j); } while ((st >> 34) != epoch);
+                const unsigned incl = __ballot_sync(0xffffffffu, ((st >> 32) & 3ull) == 2ull);
+                const unsigned first = incl ? (unsigned)__ffs(incl) - 1u : 32u;          // nearest chunk with an inclusive prefix
+                unsigned v0 = lane <= first ? (unsigned)st : 0u;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v0 += __shfl_xor_sync(0xffffffffu, v0, d);
+                prefix += v0;
+                if (incl) break;
+                j0 -= 32;
+            }
+            if (lane == 0u) atomicExch(status + bid, tag | (2ull << 32) | (unsigned long long)(prefix + total));
+        }
+        if (lane == 0u) {
+            s_prefix = prefix;
+            if (bid == gridDim.x - 1u) out[n] = prefix + total;             // grand total
+        }
+    }
+    __syncthreads();
+    ex += s_prefix;
+    if (base + SCAN1_ITEMS <= n) {
+#pragma unroll
+        for (unsigned k = 0; k < SCAN1_ITEMS; k += 4) {
+            uint4 o;
+            o.x = ex; ex += v[k]; o.y = ex; ex += v[k + 1]; o.z = ex; ex += v[k + 2]; o.w = ex; ex += v[k + 3];
+            *reinterpret_cast<uint4*>(out + base + k) = o;
+        }
+    } else {
+#pragma unroll
+        for (unsigned k = 0; k < SCAN1_ITEMS; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    }
+}
+
 // ---- counting sort ---------------------------------------------------------------------------------------------
 // pos4.w is not used by the search.
 __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_hash(const Real4* __restrict__ pos, unsigned n, GridDesc g,
@@ -132,6 +208,10 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_cell_fix_order(const unsigned* 
                                                                   const unsigned* __restrict__ fine, unsigned* __restrict__ sorted_idx)
 {
     const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;
+    {   // most of a table is air: a CTA whose entries hold nothing leaves after two loads
+        const unsigned c0 = blockIdx.x * blockDim.x, c1 = min(c0 + blockDim.x, num_keys);
+        if (__ldg(cell_start + c0) == __ldg(cell_start + c1)) return;
+    }
     if (c >= num_keys) return;
     const unsigned s = cell_start[c], e = cell_start[c + 1];
     for (unsigned a = s + 1; a < e; ++a) {
@@ -172,6 +252,43 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_reorder(unsigned n, const unsig
     kappav_out[i] = kappav_in[s];
     id_out[i] = id_in[s];
     state_out[i] = state_in[s];
+}
+
+// k_cell_fix_order + k_reorder in one pass for the fluid set: the thread of scattered slot a finds the rank of its particle
+// inside its table entry by comparing (x-order key, source index) with the entry's other particles -- entries hold one to
+// three particles, and every thread works, where the per-entry insertion sort left most lanes idle behind dependent
+// loads -- and moves the particle's state straight to its final slot.  Same permutation as the two kernels.
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_fix_reorder(unsigned n, const unsigned* __restrict__ scattered_idx, const unsigned* __restrict__ key,
+    const unsigned* __restrict__ fine, const unsigned* __restrict__ cell_start, unsigned* __restrict__ sorted_idx_out,
+    const Real4* __restrict__ pos_in, const Real4* __restrict__ vel_in, const Real* __restrict__ kappa_in, const Real* __restrict__ kappav_in,
+    const unsigned* __restrict__ id_in, const unsigned* __restrict__ state_in,
+    Real4* __restrict__ pos_out, Real4* __restrict__ vel_out, Real* __restrict__ kappa_out, Real* __restrict__ kappav_out,
+    unsigned* __restrict__ id_out, unsigned* __restrict__ state_out, Real4* __restrict__ acc_sentinel)
+{
+    const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    if (a == 0) {   // sentinel particle [n], see k_reorder
+        st_real4(pos_out + n, make_real4((Real)1.0e15, (Real)1.0e15, (Real)1.0e15, (Real)0.0));
+        st_real4(vel_out + n, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+        st_real4(acc_sentinel + n, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+    }
+    const unsigned v = scattered_idx[a];
+    const Real4 p = ld_gather(pos_in + v), u = ld_gather(vel_in + v);
+    const Real k1 = kappa_in[v], k2 = kappav_in[v];
+    const unsigned id = id_in[v], st = state_in[v];
+    const unsigned c = key[v];
+    const unsigned s = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
+    const unsigned long long kv = ((unsigned long long)fine[v] << 32) | v;
+    unsigned rank = 0;
+    for (unsigned b = s; b < e; ++b) {
+        const unsigned w = scattered_idx[b];
+        rank += ((((unsigned long long)fine[w] << 32) | w) < kv) ? 1u : 0u;
+    }
+    const unsigned i = s + rank;
+    sorted_idx_out[i] = v;
+    st_real4(pos_out + i, p);
+    st_real4(vel_out + i, u);
+    kappa_out[i] = k1; kappav_out[i] = k2; id_out[i] = id; state_out[i] = st;
 }
 
 // Boundary particles are static: sorted once. bpos4 = (x, y, z, V_b)
