@@ -37,11 +37,12 @@ def make_oracle(scene, precision, kernel=4, grad_kernel=None, **params):
     return portsim.build_port_scene(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params), "port"
 
 
-def scaled_err(a, b):
-    """max |a-b| / max |b|  (0 if both are identically zero)."""
+def scaled_err(a, b, scale=None):
+    """max |a-b| / max |b|  (0 if both are identically zero).  scale: the field's scale when b is only a part of it."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
-    scale = float(np.max(np.abs(b))) if b.size else 0.0
+    if scale is None:
+        scale = float(np.max(np.abs(b))) if b.size else 0.0
     diff = float(np.max(np.abs(a - b))) if b.size else 0.0
     if scale == 0.0:
         return diff

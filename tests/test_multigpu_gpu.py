@@ -17,19 +17,21 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("prec,axis,p2p,host", [("f64", 0, "1", 0), ("f32", 2, "1", 0), ("f64", 2, "0", 0), ("f64", 0, "1", 1)])
-def test_two_slabs_reproduce_single_gpu(prec, axis, p2p, host):
+@pytest.mark.parametrize("prec,axis,p2p,host,resync", [("f64", 0, "1", 0, 0), ("f32", 2, "1", 0, 1), ("f32", 0, "1", 0, 1), ("f64", 2, "0", 0, 0),
+                                                       ("f64", 0, "1", 1, 0), ("f64", 0, "1", 0, 1)])
+def test_two_slabs_reproduce_single_gpu(prec, axis, p2p, host, resync):
     """p2p = "1": NVLink peer-memory refresh + fused all-reduce; "0": NCCL send/recv + ncclAllReduce.
     host = 1: every slab step goes through dfsph_b200_step_host (host buffers in device order, migration inside).
-    The double runs go 25 free-running steps, through the impact of the moving block on the wall; the float run stops at
-    12 steps, before the impact: collisions amplify float rounding differences (the neighbour order of a slab run differs
-    from the single-GPU run's, so sums round differently) from 3e-6 at step 12 to 3e-3 at step 25, identically with the
-    NVLink and the NCCL transport (profiles/r1_multigpu_f32_drift.md)."""
-    steps = "25" if prec == "f64" else "12"
+    resync = 0: 25 free-running steps through the impact of the moving block on the wall, fields within 1e-8 (double).
+    resync = 1: like tests/parity.py::compare_step -- every one of the 25 steps starts from the single-GPU run's state (by
+    particle id, ownership following the migration) and EVERY step's fields must agree within the per-step tolerance
+    (1e-4 float / 1e-10 double) with identical iteration counts.  The float runs use this mode: free-running float runs
+    amplify rounding differences in collisions (the neighbour order of a slab run differs from the single-GPU run's), see
+    profiles/r1_multigpu_f32_drift.md."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tools", "multigpu_check.py"), prec, "small", steps, str(axis), str(host)]
+           "--master-port", "29533", os.path.join(ROOT, "tools", "multigpu_check.py"), prec, "small", "25", str(axis), str(host), str(resync)]
     os.environ["DFSPH_B200_P2P"] = p2p
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
