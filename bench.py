@@ -302,6 +302,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     from splishsplash_b200.solver import build_b200_scene
+    from splishsplash_b200 import capi
+    # one rank = one process = one GPU: run on the CPUs of the GPU's NUMA node and take the pinned host buffers of the
+    # end-to-end leg from that node's memory (8 ranks staging through one socket do not scale)
+    numa_node = capi.load(args.precision).dfsph_b200_bind_host_numa(local_rank)
 
     dt = np.float32 if args.precision == "f32" else np.float64
     if world == 1:
@@ -424,6 +428,10 @@ def main():
     ms_e2e = ts.timer_stop()
     wall_e2e = (time.perf_counter() - t0) * 1000.0
     ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e))   # host-side copies are synchronous: take the larger of device and wall time
+    numa_nodes = [numa_node]
+    if world > 1:
+        numa_nodes = [None] * world
+        dist.all_gather_object(numa_nodes, numa_node)
     h2d = 2 * 3 * R * n_global            # x, v of every particle of the job, per step (all ranks together)
     d2h = 2 * 3 * R * n_global + R * n_global   # x, v, density
 
@@ -446,6 +454,7 @@ def main():
             "e2e": {"value": n_global * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "warmup": e2e_warm, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "dfsph_b200_step_host (C ABI, pinned host buffers)",
+                    "host_numa_node_per_rank": numa_nodes,   # dfsph_b200_bind_host_numa: CPUs + pinned memory next to each rank's GPU (-1: unknown)
                     "mean_iterations": {"divergence": float(np.mean([i[0] for i in e2e_iters])),
                                         "pressure": float(np.mean([i[1] for i in e2e_iters]))}},
             "gpu_launches": int(launches),

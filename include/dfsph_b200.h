@@ -237,6 +237,12 @@ int dfsph_b200_get_profile(dfsph_b200_ctx* ctx, double* ms /*[DFSPH_B200_PROF_CL
 int dfsph_b200_timer_start(dfsph_b200_ctx* ctx);
 int dfsph_b200_timer_stop(dfsph_b200_ctx* ctx, float* ms);
 
+/* Multi-socket hosts: move the calling thread to the CPUs of `device`'s NUMA node and prefer that node's memory for later
+ * allocations (call before dfsph_b200_alloc_pinned / before the FluidModel arrays are allocated and registered; one rank =
+ * one process = one GPU).  The reference has no counterpart (its arrays live wherever the OpenMP first touch put them).
+ * Returns the node (>= 0) or -1 if the topology is unknown or the binding is not permitted; never fails the caller. */
+int dfsph_b200_bind_host_numa(int device);
+
 /* Pinned host buffers for the host-buffer path (dfsph_b200_step_host) and an explicit stream synchronise. */
 void* dfsph_b200_alloc_pinned(size_t bytes);
 void dfsph_b200_free_pinned(void* p);

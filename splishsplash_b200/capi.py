@@ -60,7 +60,7 @@ EXPORTS = [
     "dfsph_b200_add_boundary", "dfsph_b200_compute_boundary_volume", "dfsph_b200_set_params", "dfsph_b200_get_params",
     "dfsph_b200_step", "dfsph_b200_step_host", "dfsph_b200_download", "dfsph_b200_upload", "dfsph_b200_neighbors",
     "dfsph_b200_search_and_density", "dfsph_b200_num_particles", "dfsph_b200_num_boundary_particles", "dfsph_b200_capacity",
-    "dfsph_b200_eval_kernel", "dfsph_b200_alloc_pinned", "dfsph_b200_free_pinned", "dfsph_b200_host_register",
+    "dfsph_b200_eval_kernel", "dfsph_b200_bind_host_numa", "dfsph_b200_alloc_pinned", "dfsph_b200_free_pinned", "dfsph_b200_host_register",
     "dfsph_b200_host_unregister", "dfsph_b200_synchronize",
     "dfsph_b200_set_profiling", "dfsph_b200_get_profile", "dfsph_b200_timer_start", "dfsph_b200_timer_stop",
     "dfsph_b200_comm_get_unique_id", "dfsph_b200_comm_init", "dfsph_b200_p2p_export", "dfsph_b200_p2p_import",
@@ -118,6 +118,8 @@ def load(precision: str = "f32"):
     L.dfsph_b200_capacity.argtypes = [P]
     L.dfsph_b200_capacity.restype = C.c_uint64
     L.dfsph_b200_eval_kernel.argtypes = [P, C.c_int, C.c_uint64, P, P, P]
+    L.dfsph_b200_bind_host_numa.argtypes = [C.c_int]
+    L.dfsph_b200_bind_host_numa.restype = C.c_int
     L.dfsph_b200_alloc_pinned.argtypes = [C.c_size_t]
     L.dfsph_b200_alloc_pinned.restype = P
     L.dfsph_b200_free_pinned.argtypes = [P]

@@ -1,4 +1,10 @@
 // C-ABI implementation + step orchestration of the B200 DFSPH hot path (see include/dfsph_b200.h).
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE 1   /* sched_setaffinity, CPU_SET (dfsph_b200_bind_host_numa) */
+#endif
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a [-DDFSPH_DOUBLE] -> libdfsph_b200_f32.so / libdfsph_b200_f64.so
 #include "../../include/dfsph_b200.h"
 #include "common.cuh"
@@ -15,6 +21,10 @@
 #include <vector>
 
 #ifndef M_PI
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
+#include <ctype.h>
 #define M_PI 3.14159265358979323846
 #endif
 
@@ -1776,6 +1786,48 @@ int dfsph_b200_eval_kernel(dfsph_b200_ctx* c, int kernel, uint64_t n64, const vo
     cudaFree(dr); if (dW) cudaFree(dW); if (dG) cudaFree(dG);
     if (e != cudaSuccess) { c->sticky = 1; CTX_FAIL(c, DFSPH_B200_ERR_CUDA, "eval_kernel: %s", cudaGetErrorString(e)); }
     return DFSPH_B200_OK;
+}
+
+// Host placement for the host-buffer path on multi-socket boxes: run the calling thread on the CPUs of the GPU's NUMA
+// node and prefer that node's memory, so that pinned buffers allocated afterwards are local to the GPU's PCIe root
+// (8 ranks staging through one socket's memory were the reason the end-to-end rate stopped scaling).  Plain sysfs +
+// syscalls, no libnuma.  Returns the node (>= 0), or -1 when the topology is unknown / the binding is not permitted (the
+// process then simply stays where it is).
+int dfsph_b200_bind_host_numa(int device)
+{
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* q = bus; *q; ++q) *q = (char)tolower((unsigned char)*q);
+    char path[256];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE* f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return -1;
+    // CPUs of the node, intersected with what this process may use
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) CPU_ZERO(&allowed);
+    int picked = 0;
+    if (FILE* f = fopen(path, "r")) {
+        int a, b;
+        while (fscanf(f, "%d", &a) == 1) {
+            b = a;
+            int ch = fgetc(f);
+            if (ch == '-') { if (fscanf(f, "%d", &b) != 1) b = a; ch = fgetc(f); }
+            for (int k = a; k <= b && k < CPU_SETSIZE; ++k) if (CPU_ISSET(k, &allowed)) { CPU_SET(k, &want); ++picked; }
+            if (ch != ',') break;
+        }
+        fclose(f);
+    }
+    if (picked > 0) sched_setaffinity(0, sizeof(want), &want);
+    // memory policy: prefer the node for every later allocation of this thread (MPOL_PREFERRED = 1)
+    if (node < 1024) {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(sizeof(mask) * 8));
+    }
+    return node;
 }
 
 // pinned host buffers for the host-buffer (e2e) path
