@@ -195,10 +195,13 @@ int dfsph_b200_eval_kernel(dfsph_b200_ctx* ctx, int kernel, uint64_t n, const vo
  * that); every rank then calls dfsph_b200_comm_init BEFORE dfsph_b200_set_fluid with the slab axis and its slab [slab_lo, slab_hi) (use
  * +-1e300 for the outermost faces) and passes only the particles inside its slab to set_fluid (ids = global indices).
  * All ranks must share config.domain_min/max.  dfsph_b200_step then also performs: migration of particles that left
- * the slab, the one-support-radius ghost exchange (x, v once per step; kappa and the pressure acceleration once per
- * solver iteration, overlapped with the interior computation on a second stream) over NCCL send/recv, and the all-reduce of the density-error sum, the particle count and the CFL
- * maximum, so that every rank takes identical iteration and time-step decisions.  by_id transfers and step_host are
- * not available in multi-GPU runs (download with by_id = 0 together with DFSPH_B200_FIELD_ID). */
+ * the slab and the one-support-radius ghost exchange of x and v once per step (NCCL send/recv, message sizes from an
+ * exchange of counts), and per solver iteration the refresh of the ghosts' kappa and pressure acceleration and the
+ * all-reduce of the density-error sum -- over NVLink peer memory once dfsph_b200_p2p_import has run (below), over NCCL
+ * send/recv + ncclAllReduce otherwise -- plus the all-reduce of the particle count and the CFL maximum, so that every
+ * rank takes identical iteration and time-step decisions.  Transfers in multi-GPU runs address rows in this rank's
+ * device order (by_id = 0, together with DFSPH_B200_FIELD_ID: ids are global); dfsph_b200_step_host works on slab
+ * contexts with buffers of dfsph_b200_capacity() rows in that order. */
 int dfsph_b200_comm_get_unique_id(void* id256);   /* 256 bytes: two NCCL ids (reductions/migration + halo refresh) */
 int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id256, int rank, int world_size, int axis, double slab_lo, double slab_hi);
 

@@ -814,6 +814,19 @@ int dfsph_b200_set_fluid(dfsph_b200_ctx* c, uint64_t n64, const void* x_, const 
     if (!(density0 > 0.0) || !(volume > 0.0)) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "density0 and volume must be > 0");
     const unsigned n = (unsigned)n64;
     unsigned cap = (unsigned)std::max<uint64_t>(std::max<uint64_t>(c->cfg.max_fluid_particles, n), 1);
+    // Peer-memory contexts: the neighbour ranks hold CUDA-IPC mappings of this rank's particle arrays; growing them would
+    // free the memory those mappings point at.  A restart on the same communicator has to fit the exported capacity.
+    if (c->p2p && cap > c->cap)
+        CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "set_fluid with %llu particles exceeds the capacity (%u) whose buffers the peer ranks have mapped: create the "
+                 "context with max_fluid_particles large enough, or build a new context and exchange the peer handles again", (unsigned long long)n64, c->cap);
+    if (!c->multi && id) {
+        // single GPU: by-id transfers scatter to host row id[i], so the ids must be a permutation of 0..n-1
+        std::vector<unsigned char> seen(n, 0);
+        for (unsigned i = 0; i < n; ++i) {
+            if (id[i] >= n || seen[id[i]]) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "ids must be a permutation of 0..n-1 (id[%u] = %u)", i, id[i]);
+            seen[id[i]] = 1;
+        }
+    }
     if (cap > c->cap) { int rc = alloc_fluid(c, cap); if (rc) return rc; }
     c->n = n;
     c->density0 = density0;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.parity import (ROOT, STEP_FIELDS, TOL, compare_step, conditioned_errors, dtype_of, neighbor_sets_by_id,
+from tests.parity import (ROOT, STEP_FIELDS, TOL, compare_step, conditioned_errors, dtype_of, make_oracle, neighbor_sets_by_id,
                           scaled_err)
 from splishsplash_b200 import capi, scenes
 from splishsplash_b200.solver import TimeStepDFSPH_B200, build_b200_scene
@@ -236,6 +236,87 @@ def test_ragged_last_tile_and_single_particle():
         sc = {"fluid_x": x, "boundary_x": None, "radius": 0.025}
         r = compare_step("f64", sc, steps=2)
         assert r["ok"], (n, r["summary"])
+
+
+def _neighbor_tables(sc, prec, tile_build, **kw):
+    """Neighbour lists (fluid and boundary) in TABLE ORDER after one search, with the chosen table build."""
+    old = os.environ.get("DFSPH_B200_TILE_BUILD")
+    os.environ["DFSPH_B200_TILE_BUILD"] = "1" if tile_build else "0"
+    try:
+        ts = build_b200_scene(sc, prec, **kw)
+    finally:
+        if old is None:
+            del os.environ["DFSPH_B200_TILE_BUILD"]
+        else:
+            os.environ["DFSPH_B200_TILE_BUILD"] = old
+    try:
+        ts.search_and_density()
+        out = [ts.field("id", by_id=False)]
+        for other in (0, 1):
+            c, o, i = ts.neighbors(other)
+            out += [c, i]
+        out.append(ts.field("density"))
+        return out
+    finally:
+        ts.close()
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_tile_build_writes_the_lists_of_the_one_thread_walk(prec):
+    """k_build_tiles (candidates staged in shared memory, a CTA per block part) must produce the SAME lists in the SAME
+    order as the one-thread walk over global memory it replaces -- order matters because it is the summation order of
+    every sweep.  Jittered block with walls: rows of uneven length, particles on row faces, boundary lists."""
+    dt = dtype_of(prec)
+    sc = scenes.dam_break("small", dtype=dt)
+    rng = np.random.default_rng(5)
+    sc["fluid_x"] = (sc["fluid_x"] + rng.uniform(-0.3, 0.3, sc["fluid_x"].shape) * 2 * sc["radius"]).astype(dt)
+    a = _neighbor_tables(sc, prec, True)
+    b = _neighbor_tables(sc, prec, False)
+    assert len(a[2]) > 100000                     # real lists
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+
+
+def test_tile_build_dense_block_falls_back():
+    """A block far denser than the rest state does not fit the staging buffer of k_build_tiles (5120 records per block
+    part in float): the CTA must fall back to the one-thread walk and still produce the oracle's neighbour sets."""
+    r = 0.025
+    x = scenes.fluid_lattice((24, 24, 24), 0.3 * r, (0.0, 0.0, 0.0), np.float32)      # 37x the rest density
+    sc = {"fluid_x": x, "boundary_x": None, "radius": r}
+    ref, kind = make_oracle(sc, "f32")
+    ts = TimeStepDFSPH_B200("f32", particle_radius=r, max_fluid_neighbors=1600)
+    try:
+        ts.set_fluid(x)
+        ts.search_and_density()
+        ref.search_and_density()
+        rc, ro, ri = ref.neighbors(0, 0)
+        rid = ref.ids()
+        dc, do, di = ts.neighbors(0)
+        did = ts.field("id", by_id=False)
+        a = neighbor_sets_by_id(rc, ro, ri, rid, rid)
+        b = neighbor_sets_by_id(dc, do, di, did, did)
+        assert int(dc.max()) > 1000
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    finally:
+        ts.close()
+        ref.destroy()
+
+
+def test_set_fluid_rejects_ids_that_are_no_permutation():
+    """Single GPU: by-id transfers scatter to host row id[i]."""
+    sc = scenes.dam_break("tiny")
+    ts = TimeStepDFSPH_B200("f32")
+    try:
+        ids = np.arange(len(sc["fluid_x"]), dtype=np.uint32)
+        ids[3] = ids[4]
+        with pytest.raises(capi.DFSPHError) as e:
+            ts.set_fluid(sc["fluid_x"], ids=ids)
+        assert e.value.code == capi.ERR_INVALID
+        ids[3] = len(ids)
+        with pytest.raises(capi.DFSPHError):
+            ts.set_fluid(sc["fluid_x"], ids=ids)
+    finally:
+        ts.close()
 
 
 def test_capacity_overflow_is_reported():
