@@ -1098,7 +1098,7 @@ static int exchange_ghosts_async(dfsph_b200_ctx* c, const Real4* arr, Real4* dst
 static int run_search(dfsph_b200_ctx* c)
 {
     cudaStream_t st = c->stream;
-    unsigned n = c->n;
+    unsigned n = c->n, n_sorted = c->n;
     int rc;
     if (c->multi) {
         // ---- particle migration: owned particles that left the slab go to the neighbour rank --------------------------
@@ -1145,22 +1145,24 @@ static int run_search(dfsph_b200_ctx* c)
         c->migrated_in += in_l + in_r;
         c->migrated_out += out_l + out_r;
         const unsigned n1 = n + in_l + in_r;
-        { ProfScope ps(c, DFSPH_B200_PROF_SORT); rc = cell_sort(c, c->pos[c->cur_pos], n1, c->cell_start, true); }
+        { ProfScope ps(c, DFSPH_B200_PROF_SORT); rc = cell_sort(c, c->pos[c->cur_pos], n1, c->cell_start, true, !c->fused_reorder); }
         if (rc) return rc;
+        n_sorted = n1;
         n = n1 - out_l - out_r;   // leavers sit in the dump cell behind the kept particles
         c->n = n;
     } else {
         ProfScope ps(c, DFSPH_B200_PROF_SORT);
         rc = cell_sort(c, c->pos[c->cur_pos], n, c->cell_start, false, !c->fused_reorder);
         if (rc) return rc;
+        n_sorted = n;
     }
     c->ng = c->ng_l = c->ng_r = 0;
     if (n > 0 || c->multi) {   // multi-GPU: every rank flips its buffers every step (peers address them by parity)
         const int src = c->cur, dst = 1 - c->cur;
         const int psrc = c->cur_pos, pdst = 1 - c->cur_pos;
         ProfScope ps(c, DFSPH_B200_PROF_SORT);
-        if (n > 0 && !c->multi && c->fused_reorder)
-            k_fix_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->cell_key, c->cell_fine, c->cell_start, c->cell_rank,
+        if (n > 0 && c->fused_reorder)
+            k_fix_reorder<<<div_up(n_sorted, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n_sorted, n, c->sorted_idx, c->cell_key, c->cell_fine, c->cell_start, c->cell_rank,
                 c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src], c->id[src], c->state[src],
                 c->pos[pdst], c->vel[dst], c->kappa[dst], c->kappa_v[dst], c->id[dst], c->state[dst], c->acc);
         else if (n > 0) k_reorder<<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->sorted_idx, c->pos[psrc], c->vel[src], c->kappa[src], c->kappa_v[src],
@@ -1215,9 +1217,11 @@ static int run_search(dfsph_b200_ctx* c)
                 CUDA_TRY(c, cudaFuncSetAttribute(k_build_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB_SMEM_BYTES));
                 c->tile_attr_set = true;
             }
-            k_build_tiles<<<c->nblocks * TB_PARTS, DFSPH_TB_THREADS, TB_SMEM_BYTES, st>>>(c->grid, c->nbx, c->sph.R2, n, c->multi ? 0 : 1,
+            const double gh_lo = c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, gh_hi = c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300;
+            k_build_tiles<<<c->nblocks * TB_PARTS, DFSPH_TB_THREADS, TB_SMEM_BYTES, st>>>(c->grid, c->nbx, c->sph.R2, n, 1,
                 c->pos[c->cur_pos], c->cell_start, c->tab_f, c->Kf, c->cnt_f, c->tcnt_f,
-                c->bpos, c->bcell_start, c->nb, c->tab_b, c->Kb, c->cnt_b, c->tcnt_b, n + c->ng, c->bpart_near, c->ctrl);
+                c->bpos, c->bcell_start, c->nb, c->tab_b, c->Kb, c->cnt_b, c->tcnt_b, n + c->ng, c->bpart_near, c->ctrl,
+                c->multi && c->ng > 0 ? c->slab_axis : -1, gh_lo, gh_hi);
             k_build_neighbors<false><<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
                 c->bpos, c->bcell_start, c->nb, c->bnear, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
                 c->ng, c->gcell_start, c->sorted_idx, c->slab_axis,

@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_reorder(unsigned n, const unsig
 // inside its table entry by comparing (x-order key, source index) with the entry's other particles -- entries hold one to
 // three particles, and every thread works, where the per-entry insertion sort left most lanes idle behind dependent
 // loads -- and moves the particle's state straight to its final slot.  Same permutation as the two kernels.
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_fix_reorder(unsigned n, const unsigned* __restrict__ scattered_idx, const unsigned* __restrict__ key,
+// n = sorted points (multi-GPU: including the leavers, which sit in the dump cell behind everything else), n_keep = owned ones.
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_fix_reorder(unsigned n, unsigned n_keep, const unsigned* __restrict__ scattered_idx, const unsigned* __restrict__ key,
     const unsigned* __restrict__ fine, const unsigned* __restrict__ cell_start, unsigned* __restrict__ sorted_idx_out,
     const Real4* __restrict__ pos_in, const Real4* __restrict__ vel_in, const Real* __restrict__ kappa_in, const Real* __restrict__ kappav_in,
     const unsigned* __restrict__ id_in, const unsigned* __restrict__ state_in,
@@ -267,11 +268,12 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_fix_reorder(unsigned n, const u
 {
     const unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
-    if (a == 0) {   // sentinel particle [n], see k_reorder
-        st_real4(pos_out + n, make_real4((Real)1.0e15, (Real)1.0e15, (Real)1.0e15, (Real)0.0));
-        st_real4(vel_out + n, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
-        st_real4(acc_sentinel + n, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+    if (a == 0) {   // sentinel particle [n_keep], see k_reorder
+        st_real4(pos_out + n_keep, make_real4((Real)1.0e15, (Real)1.0e15, (Real)1.0e15, (Real)0.0));
+        st_real4(vel_out + n_keep, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
+        st_real4(acc_sentinel + n_keep, make_real4((Real)0.0, (Real)0.0, (Real)0.0, (Real)0.0));
     }
+    if (a >= n_keep) return;    // slots of the dump cell: particles that left the slab
     const unsigned v = scattered_idx[a];
     const Real4 p = ld_gather(pos_in + v), u = ld_gather(vel_in + v);
     const Real k1 = kappa_in[v], k2 = kappav_in[v];
@@ -750,7 +752,8 @@ __device__ __forceinline__ unsigned tile_walk(const Real4& xi, unsigned i, Real 
 template <bool SELF>
 __device__ __forceinline__ void tile_pass(int mode, unsigned t0, unsigned t1, unsigned n, bool finish_tiles, const GridDesc& g, const TileGeom& tg, Real R2,
     const Real4* __restrict__ pos, const Real4* __restrict__ pts, const unsigned* __restrict__ cs, unsigned srec_a, unsigned rs_a, const unsigned char* rowq,
-    unsigned* __restrict__ tab, unsigned K, unsigned* __restrict__ cnt, unsigned* __restrict__ tcnt, unsigned sentinel, unsigned* overflow, unsigned* max_out)
+    unsigned* __restrict__ tab, unsigned K, unsigned* __restrict__ cnt, unsigned* __restrict__ tcnt, unsigned sentinel, unsigned* overflow, unsigned* max_out,
+    int slab_axis, double ghost_lo, double ghost_hi)
 {
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, nw = blockDim.x >> 5;
     unsigned wmax = 0u;
@@ -759,12 +762,19 @@ __device__ __forceinline__ void tile_pass(int mode, unsigned t0, unsigned t1, un
         const bool active = i >= t0 && i < t1;
         unsigned* my = tab + (size_t)(base >> 5) * K * DFSPH_TILE + lane;
         unsigned c = 0u;
-        if (active && mode != 0) {
+        bool ghosts = false;      // multi-GPU: this particle can have ghost neighbours, which k_build_neighbors<false> appends
+        if (active && (mode != 0 || slab_axis >= 0)) {
             const Real4 xi = ld_gather(pos + i);
-            if (mode == 1) c = tile_walk<SELF>(xi, i, R2, tile_locate(xi, rowq[i - t0], tg), srec_a, rs_a, my, K);
+            if (slab_axis >= 0) {
+                const double a = slab_axis == 0 ? (double)xi.x : (slab_axis == 1 ? (double)xi.y : (double)xi.z);
+                ghosts = a < ghost_lo || a > ghost_hi;
+            }
+            if (mode == 0) { }
+            else if (mode == 1) c = tile_walk<SELF>(xi, i, R2, tile_locate(xi, rowq[i - t0], tg), srec_a, rs_a, my, K);
             else c = search_cells<SELF, false>(xi, i, g, R2, pts, cs, tab, K, base >> 5, lane);
         }
-        const bool whole = finish_tiles && base >= t0 && (base + 32u <= t1 || t1 == n);   // no other CTA has particles in this tile
+        const bool whole = finish_tiles && base >= t0 && (base + 32u <= t1 || t1 == n)   // no other CTA has particles in this tile
+                           && !__any_sync(0xffffffffu, ghosts);
         if (whole) {
             const unsigned sc = c < K ? c : K;
             if (c > K) atomicMax(overflow, c);
@@ -786,11 +796,12 @@ __device__ __forceinline__ void tile_pass(int mode, unsigned t0, unsigned t1, un
     }
 }
 
-// finish_tiles = 0 (multi-GPU: ghost neighbours are appended afterwards): every tile is left to k_build_neighbors<false>.
+// slab_axis >= 0 (multi-GPU): tiles with a particle within one cell of a slab face (outside [ghost_lo, ghost_hi]) are left
+// to k_build_neighbors<false>, which appends the ghost neighbours first.
 __global__ void __launch_bounds__(DFSPH_TB_THREADS, 2) k_build_tiles(GridDesc g, unsigned nbx, Real R2, unsigned n, int finish_tiles,
     const Real4* __restrict__ pos, const unsigned* __restrict__ cs, unsigned* __restrict__ tab_f, unsigned Kf, unsigned* __restrict__ cnt_f, unsigned* __restrict__ tcnt_f,
     const Real4* __restrict__ bpos, const unsigned* __restrict__ bcs, unsigned nb, unsigned* __restrict__ tab_b, unsigned Kb, unsigned* __restrict__ cnt_b, unsigned* __restrict__ tcnt_b,
-    unsigned sentinel_f, const unsigned char* __restrict__ bpart_near, Ctrl* ctrl)
+    unsigned sentinel_f, const unsigned char* __restrict__ bpart_near, Ctrl* ctrl, int slab_axis, double ghost_lo, double ghost_hi)
 {
     extern __shared__ __align__(16) unsigned char tb_smem[];
     Real4* srec = reinterpret_cast<Real4*>(tb_smem);
@@ -809,11 +820,11 @@ __global__ void __launch_bounds__(DFSPH_TB_THREADS, 2) k_build_tiles(GridDesc g,
     // ---- fluid-fluid lists ----------------------------------------------------------------------------------------------
     const unsigned staged = tile_stage(g, tg, pos, cs, srec, rs, tr, rowq, t0);
     tile_pass<true>(staged <= DFSPH_TB_CAP && fits ? 1 : 2, t0, t1, n, finish_tiles != 0, g, tg, R2, pos, pos, cs, srec_a, rs_a, rowq,
-                    tab_f, Kf, cnt_f, tcnt_f, sentinel_f, &ctrl->overflow, &ctrl->max_nbr);
+                    tab_f, Kf, cnt_f, tcnt_f, sentinel_f, &ctrl->overflow, &ctrl->max_nbr, slab_axis, ghost_lo, ghost_hi);
     // ---- boundary lists (nb == 0: all empty) ------------------------------------------------------------------------------
     const unsigned staged_b = (nb == 0u || !bpart_near[blockIdx.x]) ? 0u : tile_stage(g, tg, bpos, bcs, srec, rs, tr, nullptr, t0);
     tile_pass<false>(staged_b == 0u ? 0 : (staged_b <= DFSPH_TB_CAP && fits ? 1 : 2), t0, t1, n, finish_tiles != 0, g, tg, R2, pos, bpos, bcs, srec_a, rs_a, rowq,
-                     tab_b, Kb, cnt_b, tcnt_b, nb, &ctrl->overflow_b, nullptr);
+                     tab_b, Kb, cnt_b, tcnt_b, nb, &ctrl->overflow_b, nullptr, -1, 0.0, 0.0);
 }
 
 // Static boundaries: marks every cell that has a boundary particle in its 3x3x3 neighbourhood, so that the table build
