@@ -176,6 +176,7 @@ struct SphConst {
     int w_kind, g_kind;
     Real gen_k[4], gen_l[4];
     Real g_a, g_b, g_ml;   // cubic gradient in the form the float sweeps evaluate: 3 l / R^2, -2 l / R^2, -l
+    Real gV_a, gV_b, gV_ml; // the same three times the particle volume V (pass A / B / the init sweeps need V gradW, never gradW alone)
 };
 
 // Solver control block, resident in device memory so that no host round trip is needed inside a step.

@@ -260,6 +260,7 @@ static int setup_constants(dfsph_b200_ctx* c)
     s.g_ml = -s.l;
     s.W_zero = host_cubic_W(0, radius, s.k);
     s.V = static_cast<Real>(c->volume);
+    s.gV_a = s.g_a * s.V; s.gV_b = s.g_b * s.V; s.gV_ml = s.g_ml * s.V;
     s.density0 = static_cast<Real>(c->density0);
 
     // lookup tables (PrecomputedKernel<CubicKernel, 10000>)

@@ -99,27 +99,52 @@ __device__ __forceinline__ Real4 gather4(const Real4* __restrict__ base, cudaTex
     return PLAIN ? ld_plain(base + j) : ld_gather(base + j);
 }
 
-__device__ __forceinline__ const unsigned* tab_ptr(const unsigned* tab, unsigned K, unsigned i)
+// Table rows of particle i: a CTA-uniform 64-bit base (first tile of the CTA) plus a 32-bit per-thread element offset, so that
+// the sweep loop addresses the index rows as [uniform register + 32-bit register] and advances one integer per batch (with a
+// per-thread 64-bit pointer the compiler re-derived the address from the kernel parameters in every batch: ~10 of the 120
+// instructions of a 4-pair batch of pass A).  CTAs start at multiples of 32 particles (block sizes are multiples of 32).
+#ifndef DFSPH_TAB_UNIFORM
+#define DFSPH_TAB_UNIFORM 1
+#endif
+struct TabRows { const unsigned* base; unsigned off; };
+__device__ __forceinline__ TabRows tab_rows(const unsigned* tab, unsigned K, unsigned i)
 {
-    return tab + (size_t)(i >> 5) * K * DFSPH_TILE + (i & 31u);
+#if !DFSPH_TAB_UNIFORM
+    return TabRows{tab + (size_t)(i >> 5) * K * DFSPH_TILE + (i & 31u), 0u};
+#endif
+    const unsigned tile0 = (blockIdx.x * blockDim.x) >> 5;          // uniform over the CTA
+    TabRows r;
+    r.base = tab + (size_t)tile0 * K * DFSPH_TILE;
+    r.off = ((i >> 5) - tile0) * K * DFSPH_TILE + (i & 31u);
+    return r;
+}
+// kernels that run over an index list (multi-GPU export lists) have no CTA-uniform tile
+__device__ __forceinline__ TabRows tab_rows_any(const unsigned* tab, unsigned K, unsigned i)
+{
+    TabRows r;
+    r.base = tab + (size_t)(i >> 5) * K * DFSPH_TILE;
+    r.off = i & 31u;
+    return r;
 }
 
 // Warp-uniform neighbour sweep: U gathers in flight per thread, table indices of the next batch prefetched while the
 // current batch is processed.  F provides  Data load(unsigned j)  and  void apply(const Data&).
 template <int U, class F>
-__device__ __forceinline__ void neighbor_sweep(const unsigned* __restrict__ t, unsigned count, F& f)
+__device__ __forceinline__ void neighbor_sweep(const TabRows t, unsigned count, F& f)
 {
     if (count == 0) return;
     unsigned jn[U];
+    unsigned o = t.off;
 #pragma unroll
-    for (int u = 0; u < U; ++u) jn[u] = __ldg(t + (size_t)u * DFSPH_TILE);
+    for (int u = 0; u < U; ++u) jn[u] = __ldg(t.base + o + u * DFSPH_TILE);
     for (unsigned k = 0; k < count; k += U) {
         typename F::Data d[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) d[u] = f.load(jn[u], u);
+        o += U * DFSPH_TILE;
         if (k + U < count) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) jn[u] = __ldg(t + (size_t)(k + U + u) * DFSPH_TILE);
+            for (int u = 0; u < U; ++u) jn[u] = __ldg(t.base + o + u * DFSPH_TILE);
         }
         // pair geometry + kernel evaluation for the whole batch first (in lookup-table mode this issues the table
         // reads of all U pairs before any of them is consumed), then the accumulation
@@ -253,7 +278,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphCo
     const Real V = c.V;
 
     InitFluidF<MODE> ff(f, c, xi, vi);
-    neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], ff);
+    neighbor_sweep<DFSPH_U2>(tab_rows(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], ff);
     Real dadv = ff.dadv;
 #if DFSPH_REAL_IS_DOUBLE
     dadv *= V;   // "assumes that all fluid particles have the same volume" (TimeStepDFSPH.cpp:1266-1267)
@@ -261,7 +286,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_init_sweep(FluidArrays f, SphCo
 
     // Akinci2012 boundary neighbours (static bodies: v_b = 0)
     InitBoundaryF<MODE> fb(bpos, c, xi, vi);
-    neighbor_sweep<DFSPH_U1>(tab_ptr(f.tab_b, f.Kb, i), f.tcnt_b[i >> 5], fb);
+    neighbor_sweep<DFSPH_U1>(tab_rows(f.tab_b, f.Kb, i), f.tcnt_b[i >> 5], fb);
     dadv += fb.dadv;
 
     // density (TimeStep.cpp:70,110 / 133,166)
@@ -311,7 +336,11 @@ struct AccelF {
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+#if DFSPH_REAL_IS_DOUBLE
         d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+#else
+        d.g = sph_V_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);   // V gradW scale
+#endif
     }
     __device__ __forceinline__ void apply(const Data& d)
     {
@@ -323,17 +352,17 @@ struct AccelF {
             ax += s * rx; ay += s * ry; az += s * rz;
         }
 #else
-        const Real s = (g * c.V) * pSum;    // delta_ai -= V_gradW * pSum (TimeStepDFSPH.cpp:987)
+        const Real s = g * pSum;            // delta_ai -= V_gradW * pSum (TimeStepDFSPH.cpp:987); g = V gradW scale
         ax -= s * rx; ay -= s * ry; az -= s * rz;
 #endif
     }
 };
 
 template <int MODE>
-__device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphConst& c, unsigned i, const Real4 xi, Real& ax, Real& ay, Real& az)
+__device__ __forceinline__ void pressure_accel(const FluidArrays& f, const SphConst& c, unsigned i, const Real4 xi, Real& ax, Real& ay, Real& az, bool listed = false)
 {
     AccelF<MODE> fa(f, c, xi);
-    neighbor_sweep<DFSPH_U1>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fa);
+    neighbor_sweep<DFSPH_U1>(listed ? tab_rows_any(f.tab_f, f.Kf, i) : tab_rows(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fa);
     ax = fa.ax; ay = fa.ay; az = fa.az;
     const Real ki = xi.w;
     if (real_abs(ki) > DFSPH_EPS) {          // boundary term (:993-1010 / 1333-1345): a_i -= kappa_i * G_i
@@ -366,7 +395,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK, DFSPH_ACCEL_MIN_BLOCKS) k_accel(F
     else { if (i >= f.n) return; if (skip && skip[i]) return; }
     Real ax, ay, az;
     const Real4 xi = ld_gather(f.pos + i);
-    pressure_accel<MODE>(f, c, i, xi, ax, ay, az);
+    pressure_accel<MODE>(f, c, i, xi, ax, ay, az, list != nullptr);
     if (f.state[i] != 0u) { ax = ay = az = (Real)0.0; }
     st_real4(f.acc + i, make_real4(ax, ay, az, (Real)0.0));
 }
@@ -394,7 +423,11 @@ struct JacobiF {
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+#if DFSPH_REAL_IS_DOUBLE
         d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+#else
+        d.g = sph_V_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);   // V gradW scale
+#endif
     }
     __device__ __forceinline__ void apply(const Data& d)
     {
@@ -402,7 +435,7 @@ struct JacobiF {
 #if DFSPH_REAL_IS_DOUBLE
         sum += (ai.x - d.a.x) * (g * rx) + (ai.y - d.a.y) * (g * ry) + (ai.z - d.a.z) * (g * rz);
 #else
-        const Real s = g * c.V;
+        const Real s = g;   // V gradW scale
         sum += (ai.x - d.a.x) * (rx * s) + (ai.y - d.a.y) * (ry * s) + (ai.z - d.a.z) * (rz * s);
 #endif
     }
@@ -453,7 +486,7 @@ __global__ void __launch_bounds__(DFSPH_JACOBI_BLOCK, DFSPH_JACOBI_MIN_BLOCKS) k
         const Real4 xi = ld_plain(f.pos + i);
         const Real4 ai = ld_gather(f.acc + i);
         JacobiF<MODE> fj(f, c, xi, ai);
-        neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fj);
+        neighbor_sweep<DFSPH_U2>(list ? tab_rows_any(f.tab_f, f.Kf, i) : tab_rows(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fj);
         Real sum = fj.sum;
 #if DFSPH_REAL_IS_DOUBLE
         sum *= c.V;
@@ -653,11 +686,11 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_viscosity_kick(FluidArrays f, S
         Real4 v = ld_gather(f.vel + i);
         const unsigned st = f.state[i];
         ViscosityF<MODE> fv(f, c, xi, v, (Real)10.0 * sp.viscosity * c.V * c.density0);
-        neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fv);
+        neighbor_sweep<DFSPH_U2>(tab_rows(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fv);
         Real ax = sp.gx + fv.ax, ay = sp.gy + fv.ay, az = sp.gz + fv.az;
         if (sp.viscosity_boundary != (Real)0.0) {
             ViscosityBoundaryF<MODE> fb(bpos, c, xi, v, (Real)10.0 * sp.viscosity_boundary * c.density0 / f.density[i]);
-            neighbor_sweep<DFSPH_U1>(tab_ptr(f.tab_b, f.Kb, i), f.tcnt_b[i >> 5], fb);
+            neighbor_sweep<DFSPH_U1>(tab_rows(f.tab_b, f.Kb, i), f.tcnt_b[i >> 5], fb);
             ax += fb.ax; ay += fb.ay; az += fb.az;
         }
         const Real tx = v.x + ax * h, ty = v.y + ay * h, tz = v.z + az * h;     // Simulation.cpp:431-439
@@ -733,7 +766,11 @@ struct VelDivF {
     __device__ __forceinline__ void prep(Data& d) const
     {
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
+#if DFSPH_REAL_IS_DOUBLE
         d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
+#else
+        d.g = sph_V_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);   // V gradW scale
+#endif
     }
     __device__ __forceinline__ void apply(const Data& d)
     {
@@ -741,7 +778,7 @@ struct VelDivF {
 #if DFSPH_REAL_IS_DOUBLE
         delta += (vi.x - d.v.x) * (g * rx) + (vi.y - d.v.y) * (g * ry) + (vi.z - d.v.z) * (g * rz);
 #else
-        const Real s = g * c.V;
+        const Real s = g;   // V gradW scale
         delta += (vi.x - d.v.x) * (rx * s) + (vi.y - d.v.y) * (ry * s) + (vi.z - d.v.z) * (rz * s);
 #endif
     }
@@ -756,7 +793,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_init(FluidArrays f, SphCo
     const Real4 xi = ld_plain(f.pos + i);
     const Real4 vi = ld_gather(f.vel + i);
     VelDivF<MODE> fv(f, c, xi, vi);
-    neighbor_sweep<DFSPH_U2>(tab_ptr(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fv);
+    neighbor_sweep<DFSPH_U2>(tab_rows(f.tab_f, f.Kf, i), f.tcnt_f[i >> 5], fv);
     Real delta = fv.delta;
 #if DFSPH_REAL_IS_DOUBLE
     delta *= c.V;
