@@ -127,6 +127,24 @@ __device__ __forceinline__ TabRows tab_rows_any(const unsigned* tab, unsigned K,
     return r;
 }
 
+// Index rows are streamed once per sweep: which cache policy the row loads use is a tuning switch (0 = read-only path,
+// 1 = evict-first `ld.global.cs`, 2 = `L1::no_allocate`), so that the streamed rows need not displace the gathered records.
+#ifndef DFSPH_IDX_LOAD
+#define DFSPH_IDX_LOAD 2
+#endif
+__device__ __forceinline__ unsigned ld_index(const unsigned* p)
+{
+#if DFSPH_IDX_LOAD == 1
+    return __ldcs(p);
+#elif DFSPH_IDX_LOAD == 2
+    unsigned v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // Warp-uniform neighbour sweep: U gathers in flight per thread, table indices of the next batch prefetched while the
 // current batch is processed.  F provides  Data load(unsigned j)  and  void apply(const Data&).
 template <int U, class F>
@@ -136,7 +154,7 @@ __device__ __forceinline__ void neighbor_sweep(const TabRows t, unsigned count, 
     unsigned jn[U];
     unsigned o = t.off;
 #pragma unroll
-    for (int u = 0; u < U; ++u) jn[u] = __ldg(t.base + o + u * DFSPH_TILE);
+    for (int u = 0; u < U; ++u) jn[u] = ld_index(t.base + o + u * DFSPH_TILE);
     for (unsigned k = 0; k < count; k += U) {
         typename F::Data d[U];
 #pragma unroll
@@ -144,7 +162,7 @@ __device__ __forceinline__ void neighbor_sweep(const TabRows t, unsigned count, 
         o += U * DFSPH_TILE;
         if (k + U < count) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) jn[u] = __ldg(t.base + o + u * DFSPH_TILE);
+            for (int u = 0; u < U; ++u) jn[u] = ld_index(t.base + o + u * DFSPH_TILE);
         }
         // pair geometry + kernel evaluation for the whole batch first (in lookup-table mode this issues the table
         // reads of all U pairs before any of them is consumed), then the accumulation

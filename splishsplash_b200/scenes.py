@@ -224,3 +224,24 @@ def rw_state_scene(dtype=np.float32):
     bnd = box_boundary([-0.5, 0.0, -0.5], [0.5, 1.5, 0.5], r, dtype)
     return {"fluid_x": fluid, "boundary_x": bnd, "radius": r, "counts": None,
             "tank_min": np.array([-0.5, 0.0, -0.5]), "tank_max": np.array([0.5, 1.5, 0.5])}
+
+
+# Solver settings of data/Scenes/DoubleDamBreak.json:15-33 (the values the scene file overrides; everything else default)
+DOUBLE_DAM_BREAK_PARAMS = dict(minIterations=2, maxIterations=100, maxError=0.05, maxIterationsV=100, maxErrorV=0.1,
+                               enableDivergenceSolver=1, cflMethod=1, cflFactor=1.0, cflMaxTimeStepSize=0.005,
+                               viscosityMethod=1, viscosity=0.01)
+
+
+def double_dam_break_scene(dtype=np.float32):
+    """BASELINE config 1 as an Akinci2012 VARIANT: the fluid blocks, particle radius and box of
+    data/Scenes/DoubleDamBreak.json (two blocks [-1.5,0,-1.5]-[-0.8,0.75,-0.8] and [0.8,0,0.8]-[1.5,0.75,1.5] ->
+    2 x 13*14*13 = 4732 particles; UnitBox scaled 3.1 at (0,1.5,0)), with the box walls sampled by boundary particles
+    instead of the shipped Bender2019 volume map (needs Discregrid, which is not in the image: SURVEY.md section 0 item 7).
+    Solver settings: DOUBLE_DAM_BREAK_PARAMS."""
+    r = 0.025
+    a = fluid_block([-1.5, 0.0, -1.5], [-0.8, 0.75, -0.8], r, dtype, dense_mode=0)
+    b = fluid_block([0.8, 0.0, 0.8], [1.5, 0.75, 1.5], r, dtype, dense_mode=0)
+    lo, hi = np.array([-1.55, -0.05, -1.55]), np.array([1.55, 3.05, 1.55])
+    bnd = box_boundary(lo, hi, r, dtype)
+    return {"fluid_x": np.ascontiguousarray(np.concatenate([a, b], axis=0)), "boundary_x": bnd, "radius": r, "counts": None,
+            "tank_min": lo, "tank_max": hi}

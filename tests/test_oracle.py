@@ -123,6 +123,18 @@ def test_fluid_block_counts_match_reference_formula():
     assert scenes.fluid_block([0, 0, 0], [0.05, 0.05, 0.05], 0.025).shape == (0, 3)   # empty block
 
 
+def test_double_dam_break_variant_scene():
+    """BASELINE config 1 (Akinci2012 variant): particle count and block placement of data/Scenes/DoubleDamBreak.json."""
+    sc = scenes.double_dam_break_scene(np.float64)
+    x = sc["fluid_x"]
+    assert x.shape == (4732, 3)
+    assert np.allclose(x.min(axis=0), [-1.45, 0.05, -1.45]) and np.allclose(x.max(axis=0), [1.45, 0.70, 1.45])
+    assert (x[:2366, 0] < 0).all() and (x[2366:, 0] > 0).all()
+    b = sc["boundary_x"]
+    assert np.allclose(b.min(axis=0), [-1.55, -0.05, -1.55]) and np.allclose(b.max(axis=0), [1.55, 3.05, 1.55])
+    assert scenes.DOUBLE_DAM_BREAK_PARAMS["viscosityMethod"] == 1 and scenes.DOUBLE_DAM_BREAK_PARAMS["maxError"] == 0.05
+
+
 def test_named_blocks_and_boundary():
     assert int(np.prod(scenes.NAMED_BLOCKS["10M"])) == 10031040
     assert int(np.prod(scenes.NAMED_BLOCKS["50M"])) == 49948672

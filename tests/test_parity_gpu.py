@@ -101,6 +101,21 @@ def test_step_parity_rw_state_scene(prec):
     assert r["ok"], r["summary"] + " " + str(r["max_err"])
 
 
+@pytest.mark.parametrize("prec,preroll", [("f32", 0), ("f64", 0), ("f32", 120), ("f64", 120)])
+def test_step_parity_double_dam_break_variant(prec, preroll):
+    """BASELINE config 1 as the labelled Akinci2012 variant (scenes.double_dam_break_scene): blocks, box, viscosity and
+    solver settings of data/Scenes/DoubleDamBreak.json; from rest and after the reference has let the two dams collapse
+    for 120 steps (the fronts are on their way to the tank centre, the divergence solver needs several iterations)."""
+    sc = scenes.double_dam_break_scene(dtype_of(prec))
+    r = compare_step(prec, sc, steps=6, preroll=preroll, check_neighbors=(preroll == 0), **scenes.DOUBLE_DAM_BREAK_PARAMS)
+    if preroll == 0:
+        assert r["neighbors_fluid_equal"] and r["neighbors_boundary_equal"], r["summary"]
+    assert r["ok"], r["summary"] + " " + str(r["max_err"])
+    # float, step 121: one particle pressed against the floor has rho_adv = 1 -/+ 1 ulp and takes the other branch of the
+    # reference's warm-start step function (tests.parity.warm_start_flips); the fields are then compared outside its reach
+    assert r.get("warm_start_flips", 0) <= 2 and all(s.get("compared_fraction", 1.0) >= 0.5 for s in r["steps"]), r["summary"]
+
+
 @pytest.mark.parametrize("prec,mu_b", [("f32", 0.0), ("f64", 0.0), ("f64", 0.02), ("f32", 0.03)])
 def test_step_parity_with_standard_viscosity(prec, mu_b):
     """Next-row f1: Viscosity_Standard (Viscosity/Viscosity_Standard.cpp) on the device, with and without the boundary
