@@ -106,6 +106,9 @@ struct dfsph_b200_ctx {
     const Real* late_vel_stage = nullptr;     // staged host velocities (id order), landed after the reorder
     Real* early_density_stage = nullptr;      // device staging + host destination of the early density download
     void* early_density_host = nullptr;
+    Real* final_x_stage = nullptr;            // step_host: the finaliser leaves packed x / v (host row order) here ...
+    Real* final_v_stage = nullptr;
+    bool final_stage_written = false;         // ... and says so (a failed or empty step does not)
     void* stage = nullptr;       // device staging for AoS transfers
     size_t stage_bytes = 0;
 
@@ -1450,7 +1453,9 @@ static int run_solver(dfsph_b200_ctx* c)
         if (rc) return rc;
     }
     Real4* pos_out = c->pos[1 - c->cur_pos];
-    { ProfScope ps(c, DFSPH_B200_PROF_PRESS_FINAL); k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out); }
+    { ProfScope ps(c, DFSPH_B200_PROF_PRESS_FINAL); k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out,
+          c->final_x_stage, c->final_v_stage, multi ? nullptr : c->id[c->cur]); }
+    c->final_stage_written = c->final_x_stage != nullptr && n > 0;
     k_step_end<<<1, 1, 0, st>>>(c->ctrl);
     c->launches += 2;
     c->cur_pos = 1 - c->cur_pos;
@@ -1665,20 +1670,27 @@ int dfsph_b200_step_host(dfsph_b200_ctx* c, void* x_inout, void* v_inout, void* 
         c->tables_valid = false;
     }
     if (density_out) { c->early_density_stage = sd; c->early_density_host = density_out; }
+    // the staged inputs are consumed before the finaliser runs (x by the sort, v after the reorder), so the finaliser can
+    // leave the packed results in the same staging rows
+    c->final_x_stage = sx; c->final_v_stage = sv; c->final_stage_written = false;
     int rc = do_step(c, stats);
+    const bool packed = c->final_stage_written;
     c->late_vel_stage = nullptr; c->early_density_host = nullptr;
+    c->final_x_stage = c->final_v_stage = nullptr; c->final_stage_written = false;
     if (rc) { cudaStreamSynchronize(cs); return rc; }
     const unsigned n1 = c->n;   // (multi-GPU: after migration)
     if (n1 > 0) {
         const unsigned g1 = div_up(n1, 256);
         const size_t b31 = (size_t)n1 * 3 * sizeof(Real);
         const unsigned* idmap = multi ? nullptr : c->id[c->cur];
-        k_pack3<<<g1, 256, 0, st>>>(c->pos[c->cur_pos], sx, n1, idmap);
+        if (!packed) {
+            k_pack3<<<g1, 256, 0, st>>>(c->pos[c->cur_pos], sx, n1, idmap);
+            k_pack3<<<g1, 256, 0, st>>>(c->vel[c->cur], sv, n1, idmap);
+        }
         CUDA_TRY(c, cudaMemcpyAsync(x_inout, sx, b31, cudaMemcpyDeviceToHost, st));
-        k_pack3<<<g1, 256, 0, st>>>(c->vel[c->cur], sv, n1, idmap);
         CUDA_TRY(c, cudaMemcpyAsync(v_inout, sv, b31, cudaMemcpyDeviceToHost, st));
     }
-    if (stats) stats->gpu_launches += (n > 0 ? (multi ? 2u : 1u) : 0u) + (n1 > 0 ? 2u : 0u);   // unpacks + packs issued here
+    if (stats) stats->gpu_launches += (n > 0 ? (multi ? 2u : 1u) : 0u) + (n1 > 0 && !packed ? 2u : 0u);   // unpacks (+ packs) issued here
     CUDA_TRY(c, cudaStreamSynchronize(cs));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     return DFSPH_B200_OK;

@@ -830,8 +830,11 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_init(FluidArrays f, SphCo
 
 // ---- pressure finaliser + advection ----------------------------------------------------------------------------------
 // Positions are written to pos_out (the other half of the double buffer): neighbours still read the old positions.
+// out_x / out_v (step_host): the new positions and velocities additionally leave as packed 3-vectors in host row order
+// (row = out_id[i], or i when out_id is null), ready for the device-to-host copies -- no separate pack kernels.
 template <int MODE>
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_press_final(FluidArrays f, SphConst c, Ctrl* ctrl, Real4* __restrict__ pos_out)
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_press_final(FluidArrays f, SphConst c, Ctrl* ctrl, Real4* __restrict__ pos_out,
+                                                            Real* __restrict__ out_x, Real* __restrict__ out_v, const unsigned* __restrict__ out_id)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= f.n) return;
@@ -851,6 +854,11 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_press_final(FluidArrays f, SphC
     Real4 xo = xi;
     if (st == 0u) { xo.x += hs * v.x; xo.y += hs * v.y; xo.z += hs * v.z; }   // :220-237 (h captured at step start)
     st_real4(pos_out + i, xo);
+    if (out_x) {
+        const size_t d = 3 * (size_t)(out_id ? out_id[i] : i);
+        out_x[d] = xo.x; out_x[d + 1] = xo.y; out_x[d + 2] = xo.z;
+        out_v[d] = v.x; out_v[d + 1] = v.y; out_v[d + 2] = v.z;
+    }
 }
 
 __global__ void k_step_begin(Ctrl* ctrl)
