@@ -51,12 +51,21 @@ ALGO_BYTES = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
 # keyed by (kernel class, precision, particles); None when no capture exists for that configuration
 NCU_TRAFFIC = {
-    # profiles/r1_ncu_10M_f32_v2_summary.csv (ncu --set full, tools/prof_run.py f32 10M 2)
-    ("jacobi_press", "f32", "10M"): 2.0707e9,
-    ("jacobi_div", "f32", "10M"): 2.0707e9,
-    ("accel", "f32", "10M"): 1.6501e9,
-    ("build_neighbors", "f32", "10M"): 1.9677e9,
-    ("init_sweep", "f32", "10M"): 2.3788e9,
+    # profiles/r2_ncu_10M_f32_summary.csv (ncu --set full, tools/prof_run.py f32 10M 1; round-2 kernels)
+    ("jacobi_press", "f32", "10M"): 2.0598e9,
+    ("jacobi_div", "f32", "10M"): 2.0615e9,
+    ("accel", "f32", "10M"): 1.6434e9,
+    ("build_neighbors", "f32", "10M"): 1.6848e9,     # k_build_tiles (the table it writes is 1.42 GB of it)
+    ("init_sweep", "f32", "10M"): 2.4320e9,
+    ("div_final", "f32", "10M"): 2.0736e9,
+    ("press_init", "f32", "10M"): 2.0929e9,
+    ("press_final", "f32", "10M"): 2.1486e9,
+    # profiles/r2_ncu_10M_f64_summary.csv (the sweeps of the double build)
+    ("jacobi_press", "f64", "10M"): 2.7672e9,
+    ("jacobi_div", "f64", "10M"): 2.7672e9,
+    ("accel", "f64", "10M"): 1.9348e9,
+    ("init_sweep", "f64", "10M"): 3.3288e9,
+    ("press_init", "f64", "10M"): 2.8783e9,
 }
 
 

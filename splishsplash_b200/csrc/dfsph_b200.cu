@@ -138,6 +138,8 @@ struct dfsph_b200_ctx {
     Real4* ghost_stage = nullptr;
     unsigned ghost_cap = 0, ng = 0, ng_l = 0, ng_r = 0, n_exp_l = 0, n_exp_r = 0;
     unsigned *exp_l = nullptr, *exp_r = nullptr, *gcell_start = nullptr;
+    unsigned* gblock_rank = nullptr;   // ghost cell table: block -> rank among the blocks in ghost reach of the slab faces (all others: one shared empty block)
+    GridDesc ggrid;                    // = grid with block_rank = gblock_rank and the (small) number of entries of the ghost table
     Real4 *send_l = nullptr, *send_r = nullptr, *send_l2 = nullptr, *send_r2 = nullptr;
     MigrantAux *aux_sl = nullptr, *aux_sr = nullptr, *aux_rl = nullptr, *aux_rr = nullptr;
     ExchangeCounts* xcnt = nullptr;       // device: [0] mine, [1] from left, [2] from right
@@ -149,6 +151,11 @@ struct dfsph_b200_ctx {
     struct ProfRec { int cls; int seq; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
+    // DFSPH_B200_TRACE=1: GPU-timeline time between phase marks of a step (host gaps included), printed at destroy
+    bool trace = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> trace_marks;
+    std::vector<std::pair<const char*, double>> trace_sum;
+    unsigned trace_steps = 0;
     double prof_ms[DFSPH_B200_PROF_CLASSES] = {0};
     uint64_t prof_count[DFSPH_B200_PROF_CLASSES] = {0};
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
@@ -170,6 +177,37 @@ struct ProfScope {
     }
     ~ProfScope() { if (b) cudaEventRecord(b, c->stream); }
 };
+
+static void trace_mark(dfsph_b200_ctx* c, const char* name)
+{
+    if (!c->trace) return;
+    cudaEvent_t e;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    c->trace_marks.push_back({name, e});
+}
+static void trace_collect(dfsph_b200_ctx* c)   // after a stream synchronise; the time up to a mark is booked under its name
+{
+    if (!c->trace || c->trace_marks.empty()) return;
+    for (size_t k = 1; k < c->trace_marks.size(); ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->trace_marks[k - 1].second, c->trace_marks[k].second);
+        const char* nm = c->trace_marks[k].first;
+        bool found = false;
+        for (auto& t : c->trace_sum) if (t.first == nm) { t.second += ms; found = true; break; }
+        if (!found) c->trace_sum.push_back({nm, (double)ms});
+    }
+    for (auto& m : c->trace_marks) c->prof_pool.push_back(m.second);
+    c->trace_marks.clear();
+    c->trace_steps++;
+}
+static void trace_print(dfsph_b200_ctx* c)
+{
+    if (!c->trace || c->trace_steps == 0) return;
+    double tot = 0; for (auto& t : c->trace_sum) tot += t.second;
+    fprintf(stderr, "[dfsph_b200 trace rank %d] %u steps, %.3f ms/step between the first and the last mark\n", c->rank, c->trace_steps, tot / c->trace_steps);
+    for (auto& t : c->trace_sum) fprintf(stderr, "[dfsph_b200 trace rank %d]   %-34s %8.3f ms/step\n", c->rank, t.first, t.second / c->trace_steps);
+}
 
 static void prof_collect(dfsph_b200_ctx* c)   // call after a stream synchronise
 {
@@ -401,6 +439,7 @@ int dfsph_b200_create(const dfsph_b200_config* cfg, dfsph_b200_ctx** out)
     c->cfg = *cfg;
     dfsph_b200_default_params(&c->par);
     c->use_graph = getenv("DFSPH_B200_NO_GRAPH") == nullptr;
+    c->trace = getenv("DFSPH_B200_TRACE") != nullptr;
     if (const char* e = getenv("DFSPH_B200_TILE_BUILD")) c->tile_build = e[0] != '0';
     if (const char* e = getenv("DFSPH_B200_SCAN")) c->scan_single_pass = e[0] != '3';
     if (const char* e = getenv("DFSPH_B200_FUSED_REORDER")) c->fused_reorder = e[0] != '0';
@@ -428,6 +467,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     if (!c) return DFSPH_B200_OK;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    trace_print(c);
     for (int k = 0; k < 2; ++k) {
         cudaFree(c->pos[k]); cudaFree(c->vel[k]); cudaFree(c->kappa[k]); cudaFree(c->kappa_v[k]); cudaFree(c->id[k]); cudaFree(c->state[k]);
     }
@@ -439,7 +479,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
     cudaFree(c->cell_key); cudaFree(c->cell_rank); cudaFree(c->cell_fine); cudaFree(c->block_rank); cudaFree(c->block_of_rank); cudaFree(c->bpart_near); cudaFree(c->sorted_idx); cudaFree(c->cell_count); cudaFree(c->cell_start);
     cudaFree(c->scan_partial); cudaFree(c->scan_status); cudaFree(c->scan_ticket); cudaFree(c->bpos); cudaFree(c->borig); cudaFree(c->bcell_start); cudaFree(c->bnear);
     cudaFree(c->lutW); cudaFree(c->lutGradW); cudaFree(c->ctrl); cudaFree(c->partial); cudaFree(c->stage);
-    cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->send_l); cudaFree(c->send_r);
+    cudaFree(c->exp_l); cudaFree(c->exp_r); cudaFree(c->gcell_start); cudaFree(c->gblock_rank); cudaFree(c->send_l); cudaFree(c->send_r);
     cudaFree(c->send_l2); cudaFree(c->send_r2); cudaFree(c->aux_sl); cudaFree(c->aux_sr); cudaFree(c->aux_rl); cudaFree(c->aux_rr);
     for (int s = 0; s < 2; ++s) if (c->peer[s].open) {
         for (int b = 0; b < 2; ++b) { cudaIpcCloseMemHandle(c->peer[s].pos[b]); cudaIpcCloseMemHandle(c->peer[s].vel[b]); }
@@ -568,6 +608,32 @@ static int setup_grid(dfsph_b200_ctx* c)
         CUDA_TRY(c, cudaMemcpy(c->block_of_rank, inv.data(), (size_t)nblocks * sizeof(unsigned), cudaMemcpyHostToDevice));
         g.block_of_rank = c->block_of_rank;
         c->nblocks = nblocks; c->nbx = nbx;
+        if (c->multi) {
+            // Ghost particles sit within one cell of a slab face, outside the slab, i.e. in the 2 halo cells at either end of the
+            // slab axis (3 are taken).  Only the blocks that hold such cells get rows in the ghost cell table, in curve order; every
+            // other block maps to ONE shared block behind them that stays empty, so that the walk finds "no candidates" there
+            // without a test.  The per-step ghost sort (memset, scan, entry fix-up) then runs over a table of a few percent of the
+            // full size (at 10 M particles per slab: 0.3 ms -> 0.03 ms per step).
+            const int a = c->slab_axis;
+            const int na = a == 0 ? g.nx : (a == 1 ? g.ny : g.nz);
+            const int bl = a == 0 ? DFSPH_BX_LOG2 : (a == 1 ? DFSPH_BY_LOG2 : DFSPH_BZ_LOG2);
+            const int halo_cells = 4;   // 2 halo cells + the rounding of the cell count + one cell of margin
+            std::vector<unsigned> grank(nblocks);
+            unsigned nh = 0;
+            for (unsigned r = 0; r < nblocks; ++r) {
+                const unsigned lin = codes[r].second;
+                const unsigned b3[3] = { lin / (nby * nbz), (lin / nbz) % nby, lin % nbz };
+                const int c0 = (int)(b3[a] << bl), c1 = std::min(na, (int)((b3[a] + 1u) << bl));   // cells [c0, c1) of the block along the slab axis
+                const bool halo = c0 < halo_cells || c1 > na - halo_cells;
+                grank[lin] = halo ? nh++ : 0xffffffffu;
+            }
+            for (unsigned lin = 0; lin < nblocks; ++lin) if (grank[lin] == 0xffffffffu) grank[lin] = nh;
+            if (dev_alloc(c, &c->gblock_rank, nblocks)) return DFSPH_B200_ERR_CUDA;
+            CUDA_TRY(c, cudaMemcpy(c->gblock_rank, grank.data(), (size_t)nblocks * sizeof(unsigned), cudaMemcpyHostToDevice));
+            c->ggrid = g;
+            c->ggrid.block_rank = c->gblock_rank;
+            c->ggrid.num_keys = (nh + 1u) * DFSPH_ENTRIES_PER_BLOCK;
+        }
     }
     c->grid = g;
     const unsigned nfine = g.num_keys;   // table entries (+ the dump cell)
@@ -592,9 +658,9 @@ static int setup_grid(dfsph_b200_ctx* c)
 // counting sort of `n` points at `pos` into the cell table `cell_start_out`; leaves the permutation in sorted_idx
 // slab: particles outside the context's slab are filed under the dump key num_keys (multi-GPU migration)
 // fix = false: the caller orders the entries itself (k_fix_reorder)
-static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* cell_start_out, bool slab = false, bool fix = true)
+static int cell_sort(dfsph_b200_ctx* c, const Real4* pos, unsigned n, unsigned* cell_start_out, bool slab = false, bool fix = true, const GridDesc* grid = nullptr)
 {
-    const GridDesc& g = c->grid;
+    const GridDesc& g = grid ? *grid : c->grid;
     cudaStream_t st = c->stream;
     const unsigned nk = g.num_keys + 1u;   // + dump cell
     CUDA_TRY(c, cudaMemsetAsync(c->cell_count, 0, (size_t)nk * sizeof(unsigned), st));
@@ -1146,11 +1212,13 @@ static int run_search(dfsph_b200_ctx* c)
             if (in_l) k_unpack_arrivals<<<div_up(in_l, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(in_l, n, c->aux_rl, c->kappa[c->cur], c->kappa_v[c->cur], c->id[c->cur], c->state[c->cur]);
             if (in_r) k_unpack_arrivals<<<div_up(in_r, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(in_r, n + in_l, c->aux_rr, c->kappa[c->cur], c->kappa_v[c->cur], c->id[c->cur], c->state[c->cur]);
         }
+        trace_mark(c, "search: leavers + count exchange + migration");
         c->migrated_in += in_l + in_r;
         c->migrated_out += out_l + out_r;
         const unsigned n1 = n + in_l + in_r;
         { ProfScope ps(c, DFSPH_B200_PROF_SORT); rc = cell_sort(c, c->pos[c->cur_pos], n1, c->cell_start, true, !c->fused_reorder); }
         if (rc) return rc;
+        trace_mark(c, "search: cell sort");
         n_sorted = n1;
         n = n1 - out_l - out_r;   // leavers sit in the dump cell behind the kept particles
         c->n = n;
@@ -1174,6 +1242,7 @@ static int run_search(dfsph_b200_ctx* c)
         c->cur = dst; c->cur_pos = pdst;
         c->launches++;
     }
+    trace_mark(c, "search: reorder");
     if (c->multi) {
         // ---- ghost layer: one cell width of the neighbouring slabs, appended behind the owned particles ---------------
         k_zero_counts<<<1, 1, 0, st>>>(c->xcnt);
@@ -1199,18 +1268,21 @@ static int run_search(dfsph_b200_ctx* c)
             c->peer_n[0] = c->h_xcnt[1].pad0; c->peer_ngl[0] = c->h_xcnt[1].pad1;
             c->peer_n[1] = c->h_xcnt[2].pad0; c->peer_ngl[1] = c->h_xcnt[2].pad1;
         }
+        trace_mark(c, "search: export lists + count exchanges");
         rc = exchange_ghosts(c, c->pos[c->cur_pos]); if (rc) return rc;
         rc = exchange_ghosts(c, c->vel[c->cur]); if (rc) return rc;
+        trace_mark(c, "search: ghost x, v");
         k_write_sentinel<<<1, 1, 0, st>>>(c->pos[c->cur_pos], c->vel[c->cur], c->acc, n + c->ng);
         if (c->ng > 0) CUDA_TRY(c, cudaMemsetAsync(c->acc + n, 0, (size_t)c->ng * sizeof(Real4), st));
         c->launches++;
         // ghost cell table (ghosts stay in arrival order; the permutation is left in sorted_idx)
-        rc = cell_sort(c, c->pos[c->cur_pos] + n, c->ng, c->gcell_start);
+        rc = cell_sort(c, c->pos[c->cur_pos] + n, c->ng, c->gcell_start, false, true, &c->ggrid);
         if (rc) return rc;
         // global particle count = divisor of the average density error
         const unsigned long long nn = n;
         CUDA_TRY(c, cudaMemcpyAsync(&c->ctrl->n_global, &nn, sizeof(nn), cudaMemcpyHostToDevice, st));
         NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->n_global, &c->ctrl->n_global, 1, ncclUint64, ncclSum, c->comm, st));
+        trace_mark(c, "search: ghost cell sort + global count");
     } else if (n == 0) {
         k_write_sentinel<<<1, 1, 0, st>>>(c->pos[c->cur_pos], c->vel[c->cur], c->acc, 0);
     }
@@ -1229,16 +1301,17 @@ static int run_search(dfsph_b200_ctx* c)
             k_build_neighbors<false><<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
                 c->bpos, c->bcell_start, c->nb, c->bnear, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
                 c->ng, c->gcell_start, c->sorted_idx, c->slab_axis,
-                c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300);
+                c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300, c->gblock_rank);
             c->launches++;
         } else
         k_build_neighbors<true><<<div_up(n, DFSPH_BLOCK), DFSPH_BLOCK, 0, st>>>(n, c->grid, c->sph.R2, c->pos[c->cur_pos], c->cell_start,
             c->bpos, c->bcell_start, c->nb, c->bnear, c->tab_f, c->Kf, c->tab_b, c->Kb, c->cnt_f, c->cnt_b, c->tcnt_f, c->tcnt_b, c->ctrl,
             c->ng, c->gcell_start, c->sorted_idx, c->slab_axis,
-            c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300);
+            c->has_left ? c->slab_lo + 1.001 / c->grid.inv_cell : -1e300, c->has_right ? c->slab_hi - 1.001 / c->grid.inv_cell : 1e300, c->gblock_rank);
         k_check_capacity<<<1, 1, 0, st>>>(c->ctrl, c->Kf, c->Kb);
         c->launches += 2;
     }
+    trace_mark(c, "search: neighbour table");
     CUDA_TRY(c, cudaGetLastError());
     c->tables_valid = true;
     return 0;
@@ -1420,10 +1493,12 @@ static int run_solver(dfsph_b200_ctx* c)
     };
 
     const bool visc = c->par.viscosity_method == 1;
+    trace_mark(c, "solver: init sweep");
     if (div) {
         // the reference's iteration is a no-op for an empty model: avg stays 0, one iteration is counted
         int rc = solve_loop(SOLVE_DIV, c->par.max_iterations_v, c->pred_iter_v);
         if (rc) return rc;
+        trace_mark(c, "solver: divergence loop");
         ProfScope ps(c, DFSPH_B200_PROF_DIV_FINAL);
         if (visc) k_div_final<MODE, true, false><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
         else k_div_final<MODE, true, true><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, sp, c->ctrl);
@@ -1445,13 +1520,16 @@ static int run_solver(dfsph_b200_ctx* c)
         NCCL_TRY(c, c->nccl.AllReduce(&c->ctrl->maxvel_bits, &c->ctrl->maxvel_bits, 1, ncclUint64, ncclMax, c->comm, st));   // CFL maximum
         int rg = exchange_ghosts(c, c->vel[c->cur]); if (rg) return rg;                                                       // kicked velocities
     }
+    trace_mark(c, "solver: div finaliser + kick + CFL/ghost v");
     k_update_time_step<<<1, 1, 0, st>>>(c->ctrl, sp);
     { ProfScope ps(c, DFSPH_B200_PROF_PRESS_INIT); k_press_init<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl); }
     c->launches += 3;
+    trace_mark(c, "solver: pressure init");
     {
         int rc = solve_loop(SOLVE_PRESS, c->par.max_iterations, c->pred_iter);
         if (rc) return rc;
     }
+    trace_mark(c, "solver: pressure loop");
     Real4* pos_out = c->pos[1 - c->cur_pos];
     { ProfScope ps(c, DFSPH_B200_PROF_PRESS_FINAL); k_press_final<MODE><<<grid, DFSPH_BLOCK, 0, st>>>(f, c->sph, c->ctrl, pos_out,
           c->final_x_stage, c->final_v_stage, multi ? nullptr : c->id[c->cur]); }
@@ -1475,6 +1553,7 @@ static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
     cudaStream_t st = c->stream;
     // divergence solver disabled -> iterationsV = 0 (TimeStepDFSPH.cpp:170)
     CUDA_TRY(c, cudaEventRecord(c->ev[0], st));
+    trace_mark(c, "(start)");
     k_step_begin<<<1, 1, 0, st>>>(c->ctrl);
     c->launches++;
     if (!c->tables_valid) { rc = run_search(c); if (rc) return rc; }
@@ -1494,11 +1573,13 @@ static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
 #endif
     if (rc) return rc;
     c->tables_valid = false;   // positions advanced; table describes the pre-advection positions (as in the reference)
+    trace_mark(c, "solver: finaliser + advection");
     CUDA_TRY(c, cudaEventRecord(c->ev[2], st));
     if (stats) {
         CUDA_TRY(c, cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         prof_collect(c);
+        trace_collect(c);
         const Ctrl& hc = *c->h_ctrl;
         memset(stats, 0, sizeof(*stats));
         stats->iterations = hc.iterations;

@@ -853,7 +853,8 @@ __global__ void __launch_bounds__(DFSPH_BLOCK, DFSPH_BUILD_MIN_BLOCKS) k_build_n
     const Real4* __restrict__ bpos, const unsigned* __restrict__ bcell_start, unsigned nb, const unsigned char* __restrict__ bnear,
     unsigned* __restrict__ tab_f, unsigned Kf, unsigned* __restrict__ tab_b, unsigned Kb,
     unsigned* __restrict__ cnt_f, unsigned* __restrict__ cnt_b, unsigned* __restrict__ tcnt_f, unsigned* __restrict__ tcnt_b, Ctrl* ctrl,
-    unsigned ng, const unsigned* __restrict__ gcell_start, const unsigned* __restrict__ gperm, int slab_axis, double ghost_lo, double ghost_hi)
+    unsigned ng, const unsigned* __restrict__ gcell_start, const unsigned* __restrict__ gperm, int slab_axis, double ghost_lo, double ghost_hi,
+    const unsigned* __restrict__ ghost_block_rank)
 {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -864,7 +865,13 @@ __global__ void __launch_bounds__(DFSPH_BLOCK, DFSPH_BUILD_MIN_BLOCKS) k_build_n
     // multi-GPU: ghost particles of the neighbouring slabs live behind the owned ones at pos[n .. n+ng)
     if (ng > 0) {
         const double a = slab_axis == 0 ? (double)xi.x : (slab_axis == 1 ? (double)xi.y : (double)xi.z);
-        if (a < ghost_lo || a > ghost_hi) cf = search_cells<false, true>(xi, i, g, R2, pos + n, gcell_start, tab_f, Kf, tile, lane, cf, gperm, n);
+        if (a < ghost_lo || a > ghost_hi) {
+            // the ghost set has its own, compact cell table: same geometry, but only the blocks in ghost reach of the slab faces
+            // have rows of their own (every other block shares one empty block), see build of ghost_block_rank
+            GridDesc gg = g;
+            gg.block_rank = ghost_block_rank;
+            cf = search_cells<false, true>(xi, i, gg, R2, pos + n, gcell_start, tab_f, Kf, tile, lane, cf, gperm, n);
+        }
     }
     unsigned cb = 0;
     if (!FLUID_PASS) cb = nb > 0 ? cnt_b[i] : 0u;
