@@ -155,7 +155,7 @@ struct dfsph_b200_ctx {
     bool trace = false;
     std::vector<std::pair<const char*, cudaEvent_t>> trace_marks;
     std::vector<std::pair<const char*, double>> trace_sum;
-    unsigned trace_steps = 0;
+    unsigned trace_steps = 0, trace_seen = 0;
     double prof_ms[DFSPH_B200_PROF_CLASSES] = {0};
     uint64_t prof_count[DFSPH_B200_PROF_CLASSES] = {0};
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
@@ -189,7 +189,8 @@ static void trace_mark(dfsph_b200_ctx* c, const char* name)
 static void trace_collect(dfsph_b200_ctx* c)   // after a stream synchronise; the time up to a mark is booked under its name
 {
     if (!c->trace || c->trace_marks.empty()) return;
-    for (size_t k = 1; k < c->trace_marks.size(); ++k) {
+    const bool skip = c->trace_seen++ < 5u;   // the first steps carry one-time costs (NCCL connections, graph instantiation)
+    for (size_t k = 1; !skip && k < c->trace_marks.size(); ++k) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->trace_marks[k - 1].second, c->trace_marks[k].second);
         const char* nm = c->trace_marks[k].first;
@@ -199,7 +200,7 @@ static void trace_collect(dfsph_b200_ctx* c)   // after a stream synchronise; th
     }
     for (auto& m : c->trace_marks) c->prof_pool.push_back(m.second);
     c->trace_marks.clear();
-    c->trace_steps++;
+    if (!skip) c->trace_steps++;
 }
 static void trace_print(dfsph_b200_ctx* c)
 {
@@ -636,7 +637,8 @@ static int setup_grid(dfsph_b200_ctx* c)
         }
     }
     c->grid = g;
-    const unsigned nfine = g.num_keys;   // table entries (+ the dump cell)
+    const unsigned nfine = c->multi ? std::max(g.num_keys, c->ggrid.num_keys) : g.num_keys;   // table entries (+ the dump cell); the ghost
+                                                                                              // table has one block more than the halo blocks
     if (nfine + 1 > c->keys_cap) {
         if (dev_alloc(c, &c->cell_count, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
         if (dev_alloc(c, &c->cell_start, (size_t)nfine + 8)) return DFSPH_B200_ERR_CUDA;
