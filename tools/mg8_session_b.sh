@@ -1,0 +1,5 @@
+set -x
+run() { name=$1; shift; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29577 bench.py --gpus 8 "$@" > gpurun_out/$name.json 2> gpurun_out/$name.err; echo "$name rc=$?"; tail -c 300 gpurun_out/$name.json; }
+run r2b_bench_8gpu_driver --steps 20 --warmup 5 --no-steady
+run r2b_bench_8gpu_default --steps 60 --warmup 30 --no-steady
+run r2b_bench_50M_strong_8gpu --particles 50M --scaling strong --steps 30 --warmup 30 --no-steady
