@@ -153,6 +153,18 @@ def test_step_parity_million_particles(prec):
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_step_parity_ten_million_particles(prec):
+    """BASELINE config 3 at full size against the reference itself (float and double builds): the 10 M-particle block, two resynced steps,
+    every field and the iteration counts (the neighbour sets are compared at 1 M; at 10 M the per-particle neighbour COUNTS
+    the density and factor fields depend on are checked through those fields)."""
+    from oracle import refsim
+    if not refsim.ref_available(prec):
+        pytest.skip("oracle/_ref not present")
+    r = compare_step(prec, scenes.dam_break("10M", dtype=dtype_of(prec)), steps=2, check_neighbors=False)
+    assert r["ok"], r["summary"] + " " + str(r["max_err"])
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
 def test_step_parity_many_iteration_regime(prec):
     """The regime the solver spends its life in: the oracle advances the collapsing block 60 steps, then five resynced
     steps are compared field by field.  maxError is tightened so that the pressure solve needs >= 15 iterations per step
