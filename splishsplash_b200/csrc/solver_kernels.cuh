@@ -129,6 +129,11 @@ __device__ __forceinline__ TabRows tab_rows_any(const unsigned* tab, unsigned K,
 
 // Index rows are streamed once per sweep: which cache policy the row loads use is a tuning switch (0 = read-only path,
 // 1 = evict-first `ld.global.cs`, 2 = `L1::no_allocate`), so that the streamed rows need not displace the gathered records.
+// Measurement build: pass A / pass B keep their index stream, gathers and stores but do no pair arithmetic (wrong physics;
+// tools/variant_bench.py compares it with the product build to show how far the sweeps are from the memory system's floor).
+#ifndef DFSPH_GATHER_ONLY
+#define DFSPH_GATHER_ONLY 0
+#endif
 #ifndef DFSPH_IDX_LOAD
 #define DFSPH_IDX_LOAD 2
 #endif
@@ -353,6 +358,9 @@ struct AccelF {
     }
     __device__ __forceinline__ void prep(Data& d) const
     {
+#if DFSPH_GATHER_ONLY
+        return;
+#endif
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
 #if DFSPH_REAL_IS_DOUBLE
         d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
@@ -362,6 +370,11 @@ struct AccelF {
     }
     __device__ __forceinline__ void apply(const Data& d)
     {
+#if DFSPH_GATHER_ONLY
+        const Real tiny = (Real)1.0e-30;   // measurement build: the memory system's share of the sweep (the pressure force vanishes)
+        ax += tiny * d.x.x; ay += tiny * d.x.y; az += tiny * (d.x.z + d.x.w);
+        return;
+#endif
         const Real rx = d.rx, ry = d.ry, rz = d.rz, g = d.g;
         const Real pSum = xi.w + d.x.w;   // density0 ratio is 1 (single phase)
 #if DFSPH_REAL_IS_DOUBLE
@@ -426,20 +439,34 @@ struct JacobiF {
     struct Data { Real4 x, a; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* acc; const SphConst& c;
     cudaTextureObject_t acc_tex, pos_tex;
+    const unsigned* rec32;
     Real4 xi, ai;
     Real sum;
-    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), acc_tex(f.acc_tex), pos_tex(f.pos_tex), xi(xi_), ai(ai_), sum(0) {}
+    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), acc_tex(f.acc_tex), pos_tex(f.pos_tex), rec32(f.tab_b), xi(xi_), ai(ai_), sum(0) {}
     __device__ __forceinline__ Data load(unsigned j, int slot) const
     {
         // The two scattered gathers of pass B: the L1 data pipe is the limiter of this kernel, and a gather through the
         // texture unit costs fewer wavefronts than LDG.128 (tools/micro/tex_bench.cu).
         Data d;
+#if DFSPH_GATHER_ONLY == 2 && !DFSPH_REAL_IS_DOUBLE
+        // measurement build: ONE 32-byte gather per pair from a combined-record array (stand-in: the boundary table's memory,
+        // contents irrelevant) instead of x_j through the LSU + a_j through the texture unit
+        double a0, a1, a2, a3;
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(a2), "=d"(a3) : "l"(reinterpret_cast<const char*>(rec32) + 32ull * j));
+        const unsigned m = 0x3fu;
+        d.x = make_real4((Real)(__double2loint(a0) & m), (Real)(__double2hiint(a0) & m), (Real)(__double2loint(a1) & m), (Real)0.0);
+        d.a = make_real4((Real)(__double2loint(a2) & m), (Real)(__double2hiint(a2) & m), (Real)(__double2loint(a3) & m), (Real)0.0);
+        return d;
+#endif
         d.x = gather4<DFSPH_TEX_POS_B != 0, true>(pos, pos_tex, j);
         d.a = gather4<DFSPH_TEX_ACC_B != 0, false>(acc, acc_tex, j);
         return d;
     }
     __device__ __forceinline__ void prep(Data& d) const
     {
+#if DFSPH_GATHER_ONLY
+        return;
+#endif
         d.rx = xi.x - d.x.x; d.ry = xi.y - d.x.y; d.rz = xi.z - d.x.z;
 #if DFSPH_REAL_IS_DOUBLE
         d.g = sph_gradW_scale<MODE>(c, d.rx * d.rx + d.ry * d.ry + d.rz * d.rz);
@@ -449,6 +476,10 @@ struct JacobiF {
     }
     __device__ __forceinline__ void apply(const Data& d)
     {
+#if DFSPH_GATHER_ONLY
+        sum += (Real)1.0e-30 * ((d.x.x + d.x.y) + (d.x.z + d.a.x) + (d.a.y + d.a.z));   // measurement build
+        return;
+#endif
         const Real rx = d.rx, ry = d.ry, rz = d.rz, g = d.g;
 #if DFSPH_REAL_IS_DOUBLE
         sum += (ai.x - d.a.x) * (g * rx) + (ai.y - d.a.y) * (g * ry) + (ai.z - d.a.z) * (g * rz);
