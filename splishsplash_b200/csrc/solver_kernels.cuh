@@ -439,10 +439,16 @@ struct JacobiF {
     struct Data { Real4 x, a; Real rx, ry, rz, g; };
     const Real4* pos; const Real4* acc; const SphConst& c;
     cudaTextureObject_t acc_tex, pos_tex;
+#if DFSPH_GATHER_ONLY == 2
     const unsigned* rec32;
+#endif
     Real4 xi, ai;
     Real sum;
-    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), acc_tex(f.acc_tex), pos_tex(f.pos_tex), rec32(f.tab_b), xi(xi_), ai(ai_), sum(0) {}
+    __device__ __forceinline__ JacobiF(const FluidArrays& f, const SphConst& c_, Real4 xi_, Real4 ai_) : pos(f.pos), acc(f.acc), c(c_), acc_tex(f.acc_tex), pos_tex(f.pos_tex),
+#if DFSPH_GATHER_ONLY == 2
+        rec32(f.tab_b),
+#endif
+        xi(xi_), ai(ai_), sum(0) {}
     __device__ __forceinline__ Data load(unsigned j, int slot) const
     {
         // The two scattered gathers of pass B: the L1 data pipe is the limiter of this kernel, and a gather through the
