@@ -94,6 +94,7 @@ struct dfsph_b200_ctx {
     // One executable graph per (solve, buffer parities); rebuilt when anything baked into the kernel arguments changes.
     struct SolveGraph { cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; unsigned n = 0; };
     SolveGraph sgraph[2][4];   // [solve][cur * 2 + cur_pos]
+    SolveGraph sgraph_slab[2][4];   // the same for slab contexts with peer memory (pushes and waits are nodes of the loop body)
     cudaStream_t capture_stream = nullptr;
     bool use_graph = true;
     double* partial = nullptr;
@@ -126,8 +127,8 @@ struct dfsph_b200_ctx {
     int dbg_skip = 0;      // timing experiments only (DFSPH_B200_DEBUG_SKIP bit 1: ghost refresh inside iterations, bit 2: error all-reduce)
     // NVLink P2P ghost refresh (peer buffers mapped through CUDA IPC)
     bool p2p = false;
-    unsigned* flags = nullptr;          // [3 arrays][2 sides] sequence numbers written by the neighbours; [6] = push ticket
-    unsigned seq[3] = {0, 0, 0};
+    unsigned* flags = nullptr;          // [3 arrays][2 sides] sequence numbers written by the neighbours; [6] = push ticket; [8 + kind] = my sequence numbers
+    PushDesc* push_desc = nullptr;      // device: this step's export counts, slot offsets in the peers' arrays, owned count
     struct Peer { Real4* pos[2] = {nullptr, nullptr}; Real4* vel[2] = {nullptr, nullptr}; Real4* acc = nullptr; unsigned* flags = nullptr; bool open = false; } peer[2];
     unsigned peer_n[2] = {0, 0}, peer_ngl[2] = {0, 0};
     double* red_val = nullptr; unsigned* red_seq = nullptr;     // my all-reduce table: val [2][MAX_RANKS], seq [MAX_RANKS]
@@ -230,10 +231,12 @@ static void destroy_textures(dfsph_b200_ctx* c);
 static void invalidate_graphs(dfsph_b200_ctx* c)
 {
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 4; ++b) {
-        dfsph_b200_ctx::SolveGraph& g = c->sgraph[a][b];
+      for (int which = 0; which < 2; ++which) {
+        dfsph_b200_ctx::SolveGraph& g = which ? c->sgraph_slab[a][b] : c->sgraph[a][b];
         if (g.exec) cudaGraphExecDestroy(g.exec);
         if (g.graph) cudaGraphDestroy(g.graph);
         g.exec = nullptr; g.graph = nullptr; g.n = 0;
+      }
     }
 }
 
@@ -487,7 +490,7 @@ int dfsph_b200_destroy(dfsph_b200_ctx* c)
         cudaIpcCloseMemHandle(c->peer[s].acc); cudaIpcCloseMemHandle(c->peer[s].flags);
     }
     for (void* p : c->red_opened) cudaIpcCloseMemHandle(p);
-    cudaFree(c->flags); cudaFree(c->red_val); cudaFree(c->red_seq);
+    cudaFree(c->flags); cudaFree(c->push_desc); cudaFree(c->red_val); cudaFree(c->red_seq);
     cudaFree(c->xcnt); cudaFree(c->exp_all); cudaFree(c->is_export); cudaFree(c->ghost_stage);
     if (c->comm2 && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comm2);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -1059,7 +1062,7 @@ static FluidArrays fluid_arrays(dfsph_b200_ctx* c)
     f.kappa = c->kappa[c->cur]; f.kappa_v = c->kappa_v[c->cur];
     f.state = c->state[c->cur]; f.nnbr = c->nnbr;
     f.tab_f = c->tab_f; f.cnt_f = c->cnt_f; f.tab_b = c->tab_b; f.cnt_b = c->cnt_b; f.tcnt_f = c->tcnt_f; f.tcnt_b = c->tcnt_b;
-    f.Kf = c->Kf; f.Kb = c->Kb; f.n = c->n;
+    f.Kf = c->Kf; f.Kb = c->Kb; f.n = c->n; f.n_dev = nullptr;
     f.acc_tex = c->acc_tex; f.pos_tex = c->pos_tex[c->cur_pos]; f.vel_tex = c->vel_tex[c->cur];
     return f;
 }
@@ -1085,41 +1088,48 @@ static int exchange_counts(dfsph_b200_ctx* c)
 // refresh one Real4 field of the ghost particles from the owning ranks (ghost slots [n, n+ng) of `arr`)
 enum { GH_POS = 0, GH_VEL = 1, GH_ACC = 2 };
 
-// P2P version: push the export values into the neighbours' ghost slots, then wait for theirs
-static int p2p_refresh(dfsph_b200_ctx* c, int kind, bool wait = true)
+// P2P version: push the export values into the neighbours' ghost slots, then wait for theirs.  Counts, slot offsets and
+// sequence numbers are read from device memory (PushDesc, flags + 8 + kind), so the same launches work inside a graph.
+#define DFSPH_PUSH_BLOCKS 96u
+struct PushArgs {
+    const Real4* src; Real4 *dst_l, *dst_r; unsigned *flag_l, *flag_r, *seq_word; const unsigned *wait_l, *wait_r;
+};
+static PushArgs push_args(const dfsph_b200_ctx* c, int kind)
 {
-    cudaStream_t st = c->stream;
-    const Real4* src = kind == GH_POS ? c->pos[c->cur_pos] : (kind == GH_VEL ? c->vel[c->cur] : c->acc);
+    PushArgs a;
+    a.src = kind == GH_POS ? c->pos[c->cur_pos] : (kind == GH_VEL ? c->vel[c->cur] : c->acc);
     auto peer_arr = [&](int side) -> Real4* {
         const dfsph_b200_ctx::Peer& p = c->peer[side];
         return kind == GH_POS ? p.pos[c->cur_pos] : (kind == GH_VEL ? p.vel[c->cur] : p.acc);
     };
-    const unsigned seq = ++c->seq[kind];
-    // my exports to the left neighbour are ITS right ghosts (behind its left ghosts); to the right neighbour its left ghosts
-    Real4* dst_l = c->has_left ? peer_arr(0) + c->peer_n[0] + c->peer_ngl[0] : nullptr;
-    Real4* dst_r = c->has_right ? peer_arr(1) + c->peer_n[1] : nullptr;
-    unsigned* flag_l = c->has_left ? c->peer[0].flags + kind * 2 + 1 : nullptr;    // I am the left neighbour's RIGHT side
-    unsigned* flag_r = c->has_right ? c->peer[1].flags + kind * 2 + 0 : nullptr;   // and the right neighbour's LEFT side
+    // my exports to the left neighbour are ITS right ghosts (behind its left ghosts); to the right neighbour its left ghosts:
+    // the offsets inside the peers' arrays are in the PushDesc
+    a.dst_l = c->has_left ? peer_arr(0) : nullptr;
+    a.dst_r = c->has_right ? peer_arr(1) : nullptr;
+    a.flag_l = c->has_left ? c->peer[0].flags + kind * 2 + 1 : nullptr;    // I am the left neighbour's RIGHT side
+    a.flag_r = c->has_right ? c->peer[1].flags + kind * 2 + 0 : nullptr;   // and the right neighbour's LEFT side
+    a.seq_word = c->flags + 8 + kind;
+    a.wait_l = c->has_left ? c->flags + kind * 2 + 0 : nullptr;
+    a.wait_r = c->has_right ? c->flags + kind * 2 + 1 : nullptr;
+    return a;
+}
+static void launch_push(dfsph_b200_ctx* c, const PushArgs& a, cudaStream_t st, unsigned blocks)
+{
+    k_push_exports<<<blocks, DFSPH_BLOCK, 0, st>>>(a.src, c->exp_l, a.dst_l, a.flag_l, c->exp_r, a.dst_r, a.flag_r, c->push_desc, a.seq_word, c->flags + 6);
+}
+static int p2p_refresh(dfsph_b200_ctx* c, int kind, bool wait = true)
+{
+    cudaStream_t st = c->stream;
+    const PushArgs a = push_args(c, kind);
     const unsigned tot = c->n_exp_l + c->n_exp_r;
-    k_push_exports<<<std::max(div_up(tot, DFSPH_BLOCK), 1u), DFSPH_BLOCK, 0, st>>>(src, c->exp_l, c->n_exp_l, dst_l, flag_l,
-        c->exp_r, c->n_exp_r, dst_r, flag_r, seq, c->flags + 6);
+    launch_push(c, a, st, std::min(std::max(div_up(tot, DFSPH_BLOCK), 1u), DFSPH_PUSH_BLOCKS));
     c->launches++;
     if (wait) {
-        k_wait_flags<<<1, 1, 0, st>>>(c->has_left ? c->flags + kind * 2 + 0 : nullptr, c->has_right ? c->flags + kind * 2 + 1 : nullptr, seq);
+        k_wait_flags<<<1, 1, 0, st>>>(a.wait_l, a.wait_r, a.seq_word);
         c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
     return 0;
-}
-
-// what a consumer kernel has to see before it reads the ghost values of `kind` (fused wait at kernel start)
-static GhostWait ghost_wait_args(const dfsph_b200_ctx* c, int kind)
-{
-    GhostWait w;
-    w.left = (c->p2p && c->has_left) ? c->flags + kind * 2 + 0 : nullptr;
-    w.right = (c->p2p && c->has_right) ? c->flags + kind * 2 + 1 : nullptr;
-    w.seq = c->seq[kind];
-    return w;
 }
 
 static int exchange_ghosts(dfsph_b200_ctx* c, Real4* arr)
@@ -1269,6 +1279,9 @@ static int run_search(dfsph_b200_ctx* c)
             if (rc) return rc;
             c->peer_n[0] = c->h_xcnt[1].pad0; c->peer_ngl[0] = c->h_xcnt[1].pad1;
             c->peer_n[1] = c->h_xcnt[2].pad0; c->peer_ngl[1] = c->h_xcnt[2].pad1;
+            k_set_push_desc<<<1, 1, 0, st>>>(c->push_desc, c->n_exp_l, c->n_exp_r, (unsigned long long)c->peer_n[0] + c->peer_ngl[0],
+                                             (unsigned long long)c->peer_n[1], n);
+            c->launches++;
         }
         trace_mark(c, "search: export lists + count exchanges");
         rc = exchange_ghosts(c, c->pos[c->cur_pos]); if (rc) return rc;
@@ -1414,8 +1427,66 @@ static int run_solver(dfsph_b200_ctx* c)
         return 0;
     };
 
+    // Slabs with peer memory, not profiling: the same WHILE graph with the ghost refreshes as nodes of the loop body --
+    //   wait kappa | pass A | push a | wait a | pass B (+ fused all-reduce + loop decision) | push kappa | k_loop_cond.
+    // Everything that changes from step to step (owned count, export counts, slot offsets in the peers' arrays, sequence
+    // numbers) is read from device memory, so one graph per buffer parity serves the whole run; the grids are sized for the
+    // context's capacity.  All ranks take the identical loop decision (the all-reduce), so they leave the loop together.
+    auto graph_loop_slab = [&](int solve) -> int {
+        dfsph_b200_ctx::SolveGraph& sg = c->sgraph_slab[solve][c->cur * 2 + c->cur_pos];
+        { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }   // warm-start kappa of the ghosts (push + wait)
+        if (!sg.exec || sg.n != c->cap) {
+            if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+            if (sg.graph) { cudaGraphDestroy(sg.graph); sg.graph = nullptr; }
+            if (!c->capture_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
+            CUDA_TRY(c, cudaGraphCreate(&sg.graph, 0));
+            cudaGraphConditionalHandle handle;
+            CUDA_TRY(c, cudaGraphConditionalHandleCreate(&handle, sg.graph, 1, cudaGraphCondAssignDefault));
+            cudaGraphNode_t n_begin, n_while;
+            {
+                cudaKernelNodeParams kp; memset(&kp, 0, sizeof(kp));
+                void* args[2] = {(void*)&c->ctrl, (void*)&solve};
+                kp.func = (void*)k_solve_begin; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = args;
+                CUDA_TRY(c, cudaGraphAddKernelNode(&n_begin, sg.graph, nullptr, 0, &kp));
+            }
+            cudaGraphNodeParams cp = {};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = handle; cp.conditional.type = cudaGraphCondTypeWhile; cp.conditional.size = 1;
+            CUDA_TRY(c, cudaGraphAddNode(&n_while, sg.graph, &n_begin, 1, &cp));
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            cudaStream_t cs = c->capture_stream;
+            FluidArrays fg = f;
+            fg.n_dev = &c->push_desc->n_local;
+            const unsigned cap = c->cap;
+            const PushArgs pa = push_args(c, GH_ACC), pk = push_args(c, GH_POS);
+            const GhostWait no_wait{nullptr, nullptr, 0u};
+            CUDA_TRY(c, cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+            k_wait_flags<<<1, 1, 0, cs>>>(pk.wait_l, pk.wait_r, pk.seq_word);
+            k_accel<MODE><<<std::max(div_up(cap, DFSPH_BLOCK), 1u), DFSPH_BLOCK, 0, cs>>>(fg, c->sph, c->ctrl, nullptr, 0u, nullptr, no_wait);
+            launch_push(c, pa, cs, DFSPH_PUSH_BLOCKS);
+            k_wait_flags<<<1, 1, 0, cs>>>(pa.wait_l, pa.wait_r, pa.seq_word);
+            const unsigned gj = std::max(div_up(cap, DFSPH_JACOBI_BLOCK), 1u);
+            if (solve == SOLVE_DIV) k_jacobi<MODE, SOLVE_DIV><<<gj, DFSPH_JACOBI_BLOCK, 0, cs>>>(fg, c->sph, sp, c->ctrl, c->partial, nullptr, 0u, nullptr, 0u, 1, no_wait, c->pr);
+            else k_jacobi<MODE, SOLVE_PRESS><<<gj, DFSPH_JACOBI_BLOCK, 0, cs>>>(fg, c->sph, sp, c->ctrl, c->partial, nullptr, 0u, nullptr, 0u, 1, no_wait, c->pr);
+            launch_push(c, pk, cs, DFSPH_PUSH_BLOCKS);
+            k_loop_cond<<<1, 1, 0, cs>>>(handle, c->ctrl);
+            cudaGraph_t captured = nullptr;
+            CUDA_TRY(c, cudaStreamEndCapture(cs, &captured));
+            CUDA_TRY(c, cudaGraphInstantiate(&sg.exec, sg.graph, 0));
+            sg.n = cap;
+        }
+        CUDA_TRY(c, cudaGraphLaunch(sg.exec, st));
+        {   // the last kappa push of the loop: the finaliser reads the ghosts' kappa
+            const PushArgs w = push_args(c, GH_POS);
+            k_wait_flags<<<1, 1, 0, st>>>(w.wait_l, w.wait_r, w.seq_word);
+        }
+        c->launches += 2;   // + 7 kernels per iteration, added from the iteration counters when the step's statistics are read
+        return 0;
+    };
+
     auto solve_loop = [&](int solve, unsigned max_it, unsigned& pred) -> int {
         if (c->use_graph && !multi && !c->profiling) return graph_loop(solve);
+        if (c->use_graph && multi && c->p2p && !c->profiling) return graph_loop_slab(solve);   // (the same decision on every rank)
         k_solve_begin<<<1, 1, 0, st>>>(c->ctrl, solve);
         c->launches++;
         unsigned launched = 0;
@@ -1434,7 +1505,7 @@ static int run_solver(dfsph_b200_ctx* c)
                     // a one-thread kernel waits for the neighbours' flags (a per-block acquire at the start of the big
                     // kernels was measured slower: system-scope acquires flush the SM's L1); pass B ends with the fused
                     // all-reduce + loop control
-                    if (seq > 0) { const GhostWait w = ghost_wait_args(c, GH_POS); k_wait_flags<<<1, 1, 0, st>>>(w.left, w.right, w.seq); c->launches++; }
+                    if (seq > 0) { const PushArgs w = push_args(c, GH_POS); k_wait_flags<<<1, 1, 0, st>>>(w.wait_l, w.wait_r, w.seq_word); c->launches++; }
                     launch_accel(nullptr, 0, nullptr, seq);
                     { int rg = p2p_refresh(c, GH_ACC, true); if (rg) return rg; }
                     launch_jacobi(solve, nullptr, 0, nullptr, 0, 1, seq, GhostWait{nullptr, nullptr, 0u}, &c->pr);
@@ -1478,8 +1549,8 @@ static int run_solver(dfsph_b200_ctx* c)
         }
         if (kappa_in_flight) { int rl = land_ghost_kappa(); if (rl) return rl; }   // final kappa of the ghosts for the finaliser
         else if (p2p_kappa_pending) {
-            const GhostWait w = ghost_wait_args(c, GH_POS);
-            k_wait_flags<<<1, 1, 0, st>>>(w.left, w.right, w.seq);
+            const PushArgs w = push_args(c, GH_POS);
+            k_wait_flags<<<1, 1, 0, st>>>(w.wait_l, w.wait_r, w.seq_word);
             c->launches++;
         }
         else if (multi) { int rg = exchange_ghosts(c, gpos); if (rg) return rg; }
@@ -1595,6 +1666,8 @@ static int do_step(dfsph_b200_ctx* c, dfsph_b200_step_stats* stats)
         stats->gpu_launches = c->launches;
         if (c->use_graph && !c->multi && !c->profiling)   // kernels launched by the loop graphs: pass A, pass B, k_loop_cond per iteration + k_solve_begin
             stats->gpu_launches += 3u * (hc.iterations + stats->iterations_v) + (c->par.enable_divergence_solver ? 2u : 1u);
+        else if (c->use_graph && c->multi && c->p2p && !c->profiling)   // slab loop graphs: + two waits and two pushes per iteration
+            stats->gpu_launches += 7u * (hc.iterations + stats->iterations_v) + (c->par.enable_divergence_solver ? 2u : 1u);
         cudaEventElapsedTime(&stats->ms_search, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&stats->ms_solver, c->ev[1], c->ev[2]);
         c->par.time_step_size = hc.h;   // what get_params reports: the device's (CFL-adapted) step size
@@ -2031,7 +2104,9 @@ int dfsph_b200_p2p_export(dfsph_b200_ctx* c, void* blob512)
     cudaSetDevice(c->cfg.device);
     if (!blob512) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "null blob");
     if (!c->multi || c->cap == 0) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "call comm_init and set_fluid first");
-    if (!c->flags) { if (dev_alloc(c, &c->flags, 8)) return DFSPH_B200_ERR_CUDA; CUDA_SOFT(c, cudaMemset(c->flags, 0, 8 * sizeof(unsigned))); }
+    // words 0..5: arrival flags (kind x side), 6: ticket of the push kernel, 8..10: sequence number per kind of refresh
+    if (!c->flags) { if (dev_alloc(c, &c->flags, 16)) return DFSPH_B200_ERR_CUDA; CUDA_SOFT(c, cudaMemset(c->flags, 0, 16 * sizeof(unsigned))); }
+    if (!c->push_desc) { if (dev_alloc(c, &c->push_desc, 1)) return DFSPH_B200_ERR_CUDA; CUDA_SOFT(c, cudaMemset(c->push_desc, 0, sizeof(PushDesc))); }
     memset(blob512, 0, 512);
     cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)blob512;
     CUDA_SOFT(c, cudaIpcGetMemHandle(&h[0], c->pos[0]));
@@ -2057,6 +2132,7 @@ int dfsph_b200_p2p_import(dfsph_b200_ctx* c, const void* blobs_all)
     cudaSetDevice(c->cfg.device);
     if (!c->multi || !c->flags) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "call p2p_export first");
     if (!blobs_all) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "null blobs");
+    invalidate_graphs(c);   // peer pointers are kernel arguments of the slab loop graphs
     if (c->world > DFSPH_MAX_RANKS) CTX_FAIL(c, DFSPH_B200_ERR_UNSUPPORTED, "peer-memory path supports up to %d ranks", DFSPH_MAX_RANKS);
     const char* all = (const char*)blobs_all;
     const void* blobs[2] = { c->has_left ? all + 512 * (c->rank - 1) : nullptr, c->has_right ? all + 512 * (c->rank + 1) : nullptr };

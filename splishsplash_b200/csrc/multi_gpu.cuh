@@ -158,20 +158,40 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
     return v;
 }
 
-__global__ void __launch_bounds__(DFSPH_BLOCK) k_push_exports(const Real4* __restrict__ src,
-    const unsigned* __restrict__ exp_l, unsigned nl, Real4* __restrict__ dst_l, unsigned* flag_l,
-    const unsigned* __restrict__ exp_r, unsigned nr, Real4* __restrict__ dst_r, unsigned* flag_r,
-    unsigned seq, unsigned* ticket)
+// What a push needs to know about this step, kept in device memory so that the launches can live in a CUDA graph: export
+// counts, the element offsets of this rank's slots in the neighbours' ghost regions, and the owned particle count (the sweep
+// kernels of the slab loop graphs read it instead of a kernel argument, because migration changes it every step).
+struct PushDesc { unsigned nl, nr; unsigned long long off_l, off_r; unsigned n_local, pad; };
+
+__global__ void k_set_push_desc(PushDesc* pd, unsigned nl, unsigned nr, unsigned long long off_l, unsigned long long off_r, unsigned n_local)
 {
-    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nl) st_real4(dst_l + k, ld_plain(src + exp_l[k]));
-    else if (k < nl + nr) st_real4(dst_r + (k - nl), ld_plain(src + exp_r[k - nl]));
+    pd->nl = nl; pd->nr = nr; pd->off_l = off_l; pd->off_r = off_r; pd->n_local = n_local; pd->pad = 0u;
+}
+
+// Sequence numbers live on the device (`seq_word`, one per kind of refresh, next to the flag words): the last block of a push
+// advances the word and publishes the new value in the neighbours' flags; a wait reads the word -- it runs behind the local
+// push of the same kind in stream order, and all ranks push in lockstep, so it expects exactly the neighbours' matching push.
+// No host-side counter: pushes and waits can be nodes of a graph (the solver loops on slabs).
+__global__ void __launch_bounds__(DFSPH_BLOCK) k_push_exports(const Real4* __restrict__ src,
+    const unsigned* __restrict__ exp_l, Real4* __restrict__ dst_l_base, unsigned* flag_l,
+    const unsigned* __restrict__ exp_r, Real4* __restrict__ dst_r_base, unsigned* flag_r,
+    const PushDesc* __restrict__ pd, unsigned* seq_word, unsigned* ticket)
+{
+    const unsigned nl = pd->nl, tot = nl + pd->nr;
+    Real4* dst_l = dst_l_base + pd->off_l;
+    Real4* dst_r = dst_r_base + pd->off_r;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < tot; k += gridDim.x * blockDim.x) {
+        if (k < nl) st_real4(dst_l + k, ld_plain(src + exp_l[k]));
+        else st_real4(dst_r + (k - nl), ld_plain(src + exp_r[k - nl]));
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(ticket, 1u);
         if (t == gridDim.x - 1) {          // every block's stores are fenced before its ticket: all data is visible
             *ticket = 0u;
+            const unsigned seq = *seq_word + 1u;
+            *seq_word = seq;
             __threadfence_system();
             if (flag_l) st_release_sys(flag_l, seq);
             if (flag_r) st_release_sys(flag_r, seq);
@@ -179,8 +199,9 @@ __global__ void __launch_bounds__(DFSPH_BLOCK) k_push_exports(const Real4* __res
     }
 }
 
-__global__ void k_wait_flags(const unsigned* f_left, const unsigned* f_right, unsigned seq)
+__global__ void k_wait_flags(const unsigned* f_left, const unsigned* f_right, const unsigned* seq_word)
 {
+    const unsigned seq = *seq_word;
     if (f_left) while ((int)(ld_acquire_sys(f_left) - seq) < 0) { }
     if (f_right) while ((int)(ld_acquire_sys(f_right) - seq) < 0) { }
     __threadfence_system();

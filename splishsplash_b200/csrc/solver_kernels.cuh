@@ -60,6 +60,7 @@ struct FluidArrays {
     const unsigned* tcnt_b;
     unsigned Kf, Kb;
     unsigned n;
+    const unsigned* n_dev;    // slab loop graphs: the owned count lives in device memory (migration changes it every step); else null
     cudaTextureObject_t acc_tex;   // linear textures over acc / pos / vel (0 = none: plain loads).  Scattered gathers through the
     cudaTextureObject_t pos_tex;   // texture unit cost fewer L1 data-pipe wavefronts than LDG.128 (profiles/r2_tex_microbench.md)
     cudaTextureObject_t vel_tex;
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(DFSPH_BLOCK, DFSPH_ACCEL_MIN_BLOCKS) k_accel(F
     ghost_wait(gw);     // ghost kappa pushed by the neighbour ranks (no-op on a single GPU)
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (list) { if (i >= list_n) return; i = list[i]; }
-    else { if (i >= f.n) return; if (skip && skip[i]) return; }
+    else { if (i >= (f.n_dev ? *f.n_dev : f.n)) return; if (skip && skip[i]) return; }
     Real ax, ay, az;
     const Real4 xi = ld_gather(f.pos + i);
     pressure_accel<MODE>(f, c, i, xi, ax, ay, az, list != nullptr);
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(DFSPH_JACOBI_BLOCK, DFSPH_JACOBI_MIN_BLOCKS) k
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active;
     if (list) { active = i < list_n; if (active) i = list[i]; }
-    else active = i < f.n && !(skip && skip[i]);
+    else active = i < (f.n_dev ? *f.n_dev : f.n) && !(skip && skip[i]);
     double err = 0.0;
     if (active) {
         const Real h = ctrl->h;
