@@ -209,9 +209,11 @@ int dfsph_b200_comm_init(dfsph_b200_ctx* ctx, const void* id256, int rank, int w
  * every rank exports a 512-byte blob of CUDA IPC handles (its particle arrays, flag words and all-reduce table), the
  * host layer all-gathers the blobs and hands every rank the full set, and from then on (a) every ghost refresh is one
  * small kernel that stores the export values straight into the neighbour's ghost slots and publishes a sequence number
- * there -- the consumer kernel spins on its local flag at its start -- and (b) the per-iteration all-reduce of the
- * density error is fused into the tail of pass B: every rank stores its partial sum into every rank's table, waits for
- * all of them and adds them up in rank order.  A solver iteration is then 4 kernel launches and no NCCL call.
+ * there -- a one-thread kernel in front of the consumer spins on the local flag; the sequence numbers, export counts and
+ * slot offsets live in device memory -- and (b) the per-iteration all-reduce of the density error is fused into the tail
+ * of pass B: every rank stores its partial sum into every rank's table, waits for all of them and adds them up in rank
+ * order.  A solver iteration is then six kernels and no NCCL call, and the solver loops run as CUDA graphs with a WHILE
+ * node exactly as on one GPU (no host synchronisation inside a solve).
  * Requires peer access between the GPUs (NVLink/NVSwitch), at most 16 ranks; if p2p_import is never called the NCCL
  * path is used. */
 int dfsph_b200_p2p_export(dfsph_b200_ctx* ctx, void* blob512);
