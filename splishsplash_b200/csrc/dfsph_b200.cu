@@ -1888,7 +1888,13 @@ int dfsph_b200_neighbors(dfsph_b200_ctx* c, int other, uint32_t* counts, uint64_
     if (n == 0) { if (offsets) offsets[0] = 0; return DFSPH_B200_OK; }
     const unsigned* cnt = other == 0 ? c->cnt_f : c->cnt_b;
     CUDA_TRY(c, cudaMemcpyAsync(counts, cnt, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_ctrl, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->h_ctrl->fatal) {   // the lists are truncated at the table capacity: say so instead of handing them out
+        c->capacity_error = true;
+        CTX_FAIL(c, DFSPH_B200_ERR_CAPACITY, "neighbour table capacity exceeded: need %u fluid / %u boundary slots (have %u / %u); "
+                 "raise max_*_neighbors and set the fluid again", c->h_ctrl->overflow, c->h_ctrl->overflow_b, c->Kf, c->Kb);
+    }
     if (!idx) return DFSPH_B200_OK;
     if (!offsets) CTX_FAIL(c, DFSPH_B200_ERR_INVALID, "offsets is NULL");
     std::vector<unsigned long long> off(n + 1);

@@ -823,7 +823,8 @@ __global__ void __launch_bounds__(DFSPH_TB_THREADS, 2) k_build_tiles(GridDesc g,
                     tab_f, Kf, cnt_f, tcnt_f, sentinel_f, &ctrl->overflow, &ctrl->max_nbr, slab_axis, ghost_lo, ghost_hi);
     // ---- boundary lists (nb == 0: all empty) ------------------------------------------------------------------------------
     const unsigned staged_b = (nb == 0u || !bpart_near[blockIdx.x]) ? 0u : tile_stage(g, tg, bpos, bcs, srec, rs, tr, nullptr, t0);
-    tile_pass<false>(staged_b == 0u ? 0 : (staged_b <= DFSPH_TB_CAP && fits ? 1 : 2), t0, t1, n, finish_tiles != 0, g, tg, R2, pos, bpos, bcs, srec_a, rs_a, rowq,
+    // (the own-row table rowq is a by-product of the fluid staging: if that did not fit, the boundary pass cannot walk the tile either)
+    tile_pass<false>(staged_b == 0u ? 0 : (staged_b <= DFSPH_TB_CAP && staged <= DFSPH_TB_CAP && fits ? 1 : 2), t0, t1, n, finish_tiles != 0, g, tg, R2, pos, bpos, bcs, srec_a, rs_a, rowq,
                      tab_b, Kb, cnt_b, tcnt_b, nb, &ctrl->overflow_b, nullptr, -1, 0.0, 0.0);
 }
 

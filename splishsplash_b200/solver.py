@@ -280,7 +280,8 @@ def build_b200_scene(scene, precision="f32", kernel=capi.KERNEL_PRECOMPUTED_CUBI
                      **params):
     """Create a TimeStepDFSPH_B200 for a ``splishsplash_b200.scenes`` scene dict (same call order as the reference
     harness oracle/refsim.build_ref_scene)."""
-    ts = TimeStepDFSPH_B200(precision, scene["radius"], kernel, device=device, grad_kernel=grad_kernel)
+    cap = {k: params.pop(k) for k in ("max_fluid_neighbors", "max_boundary_neighbors") if k in params}   # table capacities (config)
+    ts = TimeStepDFSPH_B200(precision, scene["radius"], kernel, device=device, grad_kernel=grad_kernel, **cap)
     if params:
         ts.set(**params)
     ts.set_fluid(scene["fluid_x"], scene.get("fluid_v"))

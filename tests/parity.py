@@ -133,6 +133,7 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
     keeps both numbers under "conditioned" and the result counts the fallbacks in "conditioned_fallbacks"."""
     from splishsplash_b200.solver import build_b200_scene
     tol = TOL[precision] if tol is None else tol
+    dev_only = {k: params.pop(k) for k in ("max_fluid_neighbors", "max_boundary_neighbors") if k in params}   # device table capacities
     ref, kind = make_oracle(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params)
     res = {"ok": True, "oracle": kind, "precision": precision, "steps": [], "max_err": {}}
     try:
@@ -141,7 +142,7 @@ def compare_step(precision, scene, steps=1, kernel=4, resync=True, tol=None, che
             bx, bV = ref.boundary(0)
         # boundary volumes: device-computed, checked against the reference's (then the reference's are used so that
         # the step comparison starts from identical inputs)
-        dev = build_b200_scene(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params)
+        dev = build_b200_scene(scene, precision, kernel=kernel, grad_kernel=grad_kernel, **params, **dev_only)
         try:
             if bx is not None:
                 # the reference z-sorts its boundary arrays once; match particles by position

@@ -362,6 +362,39 @@ def test_capacity_overflow_is_reported():
         ts.close()
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_dense_block_next_to_a_wall_overflows_cleanly(prec):
+    """A lattice squeezed to 2.7x the rest density next to the tank walls: the fluid rows of a block part no longer fit the
+    shared-memory tile (one-thread fallback), the boundary rows still do -- the boundary pass must not walk the tile with
+    the own-row table the fluid staging never wrote (found by tools/fuzz_parity.py: out-of-bounds shared-memory reads).
+    The lists need more than the 64 slots of the table: the export and the step both say so, nothing is truncated silently."""
+    sc = scenes.dam_break("64k", dtype=dtype_of(prec))
+    x = sc["fluid_x"].astype(np.float64)
+    x = x.min(axis=0) + 0.72 * (x - x.min(axis=0))        # squeezed towards the tank corner: stays next to three walls
+    sc = dict(sc, fluid_x=np.ascontiguousarray(x.astype(dtype_of(prec))))
+    ts = build_b200_scene(sc, prec)
+    try:
+        with pytest.raises(capi.DFSPHError) as e:
+            ts.neighbors(0)
+        assert e.value.code == capi.ERR_CAPACITY
+        with pytest.raises(capi.DFSPHError) as e:
+            ts.step(1)
+        assert e.value.code == capi.ERR_CAPACITY
+    finally:
+        ts.close()
+    # with room in the table the same state gives the oracle's neighbour sets and fields.  (The state is far outside anything
+    # a solver produces: the pressure solve runs into its 100-iteration limit on both sides; in float 100 non-converging Jacobi
+    # iterations amplify rounding beyond 1e-4 in kappa, so the float case checks the sets and everything computed before the loop.)
+    r = compare_step(prec, sc, steps=1, max_fluid_neighbors=128, max_boundary_neighbors=128)
+    assert r["neighbors_fluid_equal"] and r["neighbors_boundary_equal"], r["summary"]
+    assert r["steps"][0]["ref_iter"] == r["steps"][0]["dev_iter"], r["summary"]
+    if prec == "f64":
+        assert r["ok"], r["summary"] + " " + str(r["max_err"])
+    else:
+        for f in ("boundary volume", "density", "factor", "advected density"):
+            assert r["max_err"][f] <= TOL[prec], (f, r["max_err"])
+
+
 def test_capacity_overflow_without_statistics_freezes_the_state():
     """dfsph_b200_step(ctx, NULL) does not synchronise; a neighbour list that does not fit must still stop the step ON
     THE DEVICE (no solver pass on truncated lists, no advection) and surface at the next synchronising call."""
