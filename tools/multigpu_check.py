@@ -29,6 +29,16 @@ def main():
     # give the block an initial velocity towards +x so that particles migrate across the slab faces
     v = np.zeros_like(sc["fluid_x"]); v[:, axis] = 0.8
     sc["fluid_v"] = v
+    if os.environ.get("FUZZ_SEED"):   # randomised variant: jittered, thinned, stirred block (the same on every rank)
+        rng = np.random.default_rng(int(os.environ["FUZZ_SEED"]))
+        x = sc["fluid_x"].astype(np.float64)
+        d = 2.0 * sc["radius"]
+        x = x + float(rng.choice([0.05, 0.2, 0.35])) * d * (rng.random(x.shape) - 0.5)
+        keep = rng.random(len(x)) >= float(rng.choice([0.0, 0.1, 0.4]))
+        x = x[keep]
+        vv = v[keep].astype(np.float64) + float(rng.choice([0.0, 0.5, 2.0])) * (rng.random(x.shape) - 0.5)
+        sc["fluid_x"] = np.ascontiguousarray(x.astype(dtype_of(prec)))
+        sc["fluid_v"] = np.ascontiguousarray(vv.astype(dtype_of(prec)))
     mine = parallel.select_slab(sc, rank, world, axis=axis)
     # boundary volumes must come from the global boundary (a per-rank subset would change V near the cut)
     single = build_b200_scene(sc, prec, device=local) if True else None
