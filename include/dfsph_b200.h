@@ -174,7 +174,8 @@ int dfsph_b200_upload(dfsph_b200_ctx* ctx, dfsph_b200_field field, const void* s
  * Runs the search on the current positions if needed.  counts[n]; if idx != NULL, offsets[n+1] and idx[cap] receive a
  * CSR table (lists ascending).  Fluid rows/indices are in current device order (see FIELD_ID); boundary indices are
  * the order in which boundary particles were added.  Only for tests and non-ported host code -- the solver never
- * materialises host-visible lists. */
+ * materialises host-visible lists.  A list that exceeds max_fluid_neighbors / max_boundary_neighbors makes the call fail
+ * with DFSPH_B200_ERR_CAPACITY (like the step): truncated lists are never handed out. */
 int dfsph_b200_neighbors(dfsph_b200_ctx* ctx, int other, uint32_t* counts, uint64_t* offsets, uint32_t* idx, uint64_t cap);
 
 /* Neighbour search + density only (what ReadWriteStateTests.cpp:349-350 exercises):
